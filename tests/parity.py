@@ -1,0 +1,134 @@
+"""Shared parity machinery: replay a golden trace (or drive two backends side by side).
+
+A *backend* is anything with the small duck-typed surface below; both the CPU oracle
+(oracle.salp_oracle.OracleVecEnv) and the CUDA product (grasp_lab_salp_b200.SalpBatch)
+provide it, so every parity test reads the same for both:
+
+    .num_envs  .obs_dim
+    .set_scene_pool(targets[N,P,2], obstacles[N,P,n,2])
+    .reset(mask=None) -> obs[N,D]
+    .step(actions[N,3], auto_reset=False) -> (obs, reward, terminated, truncated)   (numpy, host)
+    .terms [N,8]  .substeps [N]  .metrics [N,20]
+    .get_state(name) -> column[N]
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from conftest import GOLDEN_DIR
+
+# golden "state" column name -> backend state column (None = not a product state column)
+STATE_MAP = {
+    "posw_x": "posw_x", "posw_y": "posw_y", "posw_z": "posw_z",
+    "vel_x": "vel_x", "vel_y": "vel_y", "vel_z": "vel_z",
+    "euler_x": "euler_x", "euler_y": "euler_y", "euler_z": "euler_z",
+    "angvel_x": "angvel_x", "angvel_y": "angvel_y", "angvel_z": "angvel_z",
+    "length": "length", "width": "width",
+    "nozzle_angle1": "nozzle_angle1", "nozzle_angle2": "nozzle_angle2", "prev_dist": "prev_dist",
+    "pos_x": "pos_x", "pos_y": "pos_y", "pos_z": "pos_z",
+    "angle_x": "angle_x", "angle_y": "angle_y", "angle_z": "angle_z",
+    "acc_x": "acc_x", "acc_y": "acc_y", "acc_z": "acc_z",
+    "angacc_x": "angacc_x", "angacc_y": "angacc_y", "angacc_z": "angacc_z", "com_x": "com_x",
+}
+# near-zero channels (out-of-plane motion, SURVEY.md hard part 5): compared with an absolute floor
+SMALL_CHANNELS = {"posw_z", "vel_z", "euler_x", "euler_y", "angvel_x", "angvel_y", "pos_z", "angle_x",
+                  "angle_y", "acc_z", "angacc_x", "angacc_y"}
+METRIC_COLS = {"path_length": 2, "direct_distance": 3, "path_efficiency": 4, "final_distance": 5,
+               "initial_distance": 6, "avg_compression": 7, "avg_coast_time": 8, "avg_nozzle_angle": 9,
+               "avg_velocity": 10, "avg_rewards_track": 11, "avg_rewards_heading": 12,
+               "avg_rewards_smooth": 13, "avg_rewards_yaw": 14, "avg_rewards_time": 15,
+               "avg_rewards_sideslip": 16, "avg_rewards_obstacle": 17}
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN_DIR, name), allow_pickle=False)
+
+
+def golden_params(g, **kw):
+    from grasp_lab_salp_b200.params import default_params
+    return default_params(refill_poly=g["refill_poly"], jet_poly=g["jet_poly"], **kw)
+
+
+def rel_err(a, b, floor):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.abs(a - b) / np.maximum(np.abs(b), floor)
+
+
+def replay_golden(backend, g, rtol, *, small_rtol=None, small_floor=1e-7, floor=1e-9, accel_rtol=None,
+                  check_metrics=True, report=None):
+    """Drive `backend` with the golden actions/scenes and compare every recorded quantity.
+
+    Integer/flag quantities (K, cycle, phase, terminated, truncated, hence reset indices)
+    must be bit-exact; floats within `rtol` relative (absolute floor `floor`; `small_floor`
+    for the near-zero out-of-plane channels).  Returns the worst relative error seen.
+    """
+    actions = g["actions"]
+    n, T, _ = actions.shape
+    assert backend.num_envs == n
+    names = [str(s) for s in g["state_names"]]
+    backend.set_scene_pool(g["targets"], g["obstacles"])
+    obs0 = backend.reset()
+    np.testing.assert_allclose(obs0, g["first_obs"], rtol=max(rtol, 1e-6), atol=1e-7)
+    worst = {}
+
+    def track(key, err):
+        worst[key] = max(worst.get(key, 0.0), float(np.max(err)) if np.size(err) else 0.0)
+
+    for t in range(T):
+        obs, rew, term, trunc = backend.step(actions[:, t], auto_reset=False)
+        ctx = f"step {t}"
+        np.testing.assert_array_equal(backend.substeps, g["K"][:, t], err_msg=f"K {ctx}")
+        np.testing.assert_array_equal(backend.get_state("cycle"), g["cycle"][:, t], err_msg=f"cycle {ctx}")
+        np.testing.assert_array_equal(backend.get_state("phase"), g["phase"][:, t], err_msg=f"phase {ctx}")
+        np.testing.assert_array_equal(term.astype(np.uint8), g["terminated"][:, t], err_msg=f"terminated {ctx}")
+        np.testing.assert_array_equal(trunc.astype(np.uint8), g["truncated"][:, t], err_msg=f"truncated {ctx}")
+        for j, nm in enumerate(names):
+            col = STATE_MAP.get(nm)
+            if col is None:
+                continue
+            ref = g["state"][:, t, j]
+            got = backend.get_state(col)
+            fl = small_floor if nm in SMALL_CHANNELS else floor
+            tol = (small_rtol or rtol) if nm in SMALL_CHANNELS else rtol
+            if nm.startswith(("acc_", "angacc_")):
+                # accelerations are finite-difference driven (differences of O(1) numbers / dt):
+                # the absolute floor scales with 1/dt^2 of the geometry's rounding noise
+                fl = max(fl, 1e-6)
+                tol = accel_rtol or rtol
+            finite = np.isfinite(ref)
+            np.testing.assert_array_equal(np.isfinite(got), finite, err_msg=f"{nm} finiteness {ctx}")
+            e = rel_err(got[finite], ref[finite], fl)
+            track(nm, e)
+            assert np.all(e <= tol), f"{nm} {ctx}: rel err {e.max():.3e} > {tol:g} (got {got}, ref {ref})"
+        fin = np.isfinite(g["reward"][:, t])
+        e = rel_err(rew[fin], g["reward"][:, t][fin], 1e-3)
+        track("reward", e)
+        assert np.all(e <= max(rtol, 1e-6) * 10), f"reward {ctx}: {e.max():.3e}"
+        tf = np.isfinite(g["terms"][:, t])
+        e = rel_err(backend.terms[:, :7][tf], g["terms"][:, t][tf], 1e-3)
+        track("reward_terms", e)
+        assert np.all(e <= max(rtol, 1e-6) * 10), f"reward terms {ctx}: {e.max():.3e}"
+        of = np.isfinite(g["obs"][:, t])
+        e = rel_err(obs[of], g["obs"][:, t][of], 1e-4)
+        track("obs", e)
+        assert np.all(e <= max(rtol, 2e-7) * 10), f"obs {ctx}: {e.max():.3e}"
+        ended = (term.astype(bool) | trunc.astype(bool))
+        if check_metrics and ended.any():
+            keys = [str(k) for k in g["metric_keys"]]
+            for j, k in enumerate(keys):
+                ref = g["metrics"][ended, t, j]
+                got = backend.metrics[ended, METRIC_COLS[k]]
+                ok = np.isfinite(ref)
+                e = rel_err(got[ok], ref[ok], 1e-6)
+                track("metrics", e)
+                assert np.all(e <= max(rtol, 1e-6) * 10), f"metric {k} {ctx}: {e.max():.3e}"
+        if ended.any():
+            obs_r = backend.reset(mask=ended.astype(np.uint8))
+            np.testing.assert_allclose(obs_r[ended], g["reset_obs"][ended, t], rtol=1e-6, atol=1e-7,
+                                       err_msg=f"post-reset obs {ctx}")
+    if report is not None:
+        report.update(worst)
+    return max(worst.values()) if worst else 0.0
