@@ -97,7 +97,7 @@ def replay_golden(backend, g, rtol, *, small_rtol=None, small_floor=1e-7, floor=
                 # accelerations are finite-difference driven (differences of O(1) numbers / dt):
                 # the absolute floor scales with 1/dt^2 of the geometry's rounding noise
                 fl = max(fl, 1e-6)
-                tol = accel_rtol or rtol
+                tol = max(tol, accel_rtol or 0.0)
             finite = np.isfinite(ref)
             np.testing.assert_array_equal(np.isfinite(got), finite, err_msg=f"{nm} finiteness {ctx}")
             e = rel_err(got[finite], ref[finite], fl)
