@@ -1,0 +1,218 @@
+"""SalpBatch: N independent SalpRobotEnv instances on one GPU, behind the C ABI.
+
+Two faces over the same handle:
+
+* host face (numpy): ``reset()`` / ``step()`` call ``salp_reset_host`` / ``salp_step_host`` --
+  H2D of the actions, the kernels, D2H of the results, one stream synchronise.  This is what
+  the SB3-VecEnv-shaped wrapper (vec_env.py) and the parity tests use.
+* device face (torch tensors, zero-copy): ``reset_device()`` / ``step_device()`` pass raw device
+  pointers to ``salp_reset`` / ``salp_step`` on the current torch stream, no synchronisation.
+  This is what rollouts and bench.py use.
+
+Semantics follow the reference's SalpRobotEnv.reset()/step() (src/salp_robot_env.py:114-155,
+196-299) per env; ``auto_reset=True`` adds what an SB3 DummyVecEnv/SubprocVecEnv worker does
+around it (reset the finished env, return the post-reset observation, keep the last observation
+of the finished episode in ``terminal_obs``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .params import (NUM_EPISODE_METRICS, NUM_REWARD_TERMS, STEP_AUTORESET, STEP_SORT_BY_K, SalpParams,
+                     default_params, field_dtype, field_id)
+
+
+def _np_ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class SalpBatch:
+    def __init__(self, num_envs: int, params: SalpParams | None = None, seed: int = 0,
+                 env_id_offset: int = 0, device: int = 0, _cdll=None):
+        self._L = _cdll if _cdll is not None else _lib.load()
+        self.params = (params or default_params()).copy()
+        self.num_envs = int(num_envs)
+        self.obs_dim = self.params.obs_dim
+        self.device = int(device)
+        h = C.c_void_p()
+        rc = self._L.salp_create(C.byref(self.params), self.num_envs, self.device, C.c_uint64(seed),
+                                 int(env_id_offset), C.byref(h))
+        if rc != 0:
+            raise _lib.SalpError(rc, (self._L.salp_last_error(None) or b"").decode())
+        self._h = h
+        n, d = self.num_envs, self.obs_dim
+        # persistent host buffers of the numpy face
+        self.obs = np.zeros((n, d), np.float32)
+        self.terminal_obs = np.zeros((n, d), np.float32)
+        self.reward = np.zeros(n, np.float32)
+        self.terminated = np.zeros(n, np.uint8)
+        self.truncated = np.zeros(n, np.uint8)
+        self.terms = np.zeros((n, NUM_REWARD_TERMS), np.float64)
+        self.substeps = np.zeros(n, np.int32)
+        self.metrics = np.zeros((n, NUM_EPISODE_METRICS), np.float64)
+        self._io_host = _lib.SalpStepIO()
+        self._dev = None          # lazily created torch output tensors of the device face
+
+    # ------------------------------------------------------------------ lifetime / errors
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.salp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise _lib.SalpError(rc, (self._L.salp_last_error(self._h) or b"").decode())
+
+    def check(self):
+        """Raise if a kernel recorded a device-side error (synchronises)."""
+        self._check(self._L.salp_check(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.salp_launch_count(self._h))
+
+    # ------------------------------------------------------------------ host (numpy) face
+    def set_scene_pool(self, targets, obstacles):
+        """Replace the built-in Philox scene sampler by caller-given scenes (parity with an
+        external oracle): targets [N,P,2], obstacles [N,P,num_obstacles,2]; None = built-in."""
+        if targets is None:
+            self._check(self._L.salp_set_scene_pool(self._h, None, None, 0))
+            return
+        targets = np.ascontiguousarray(targets, np.float32)
+        obstacles = np.ascontiguousarray(obstacles, np.float32)
+        P = targets.shape[1]
+        if targets.shape != (self.num_envs, P, 2) or obstacles.shape != (self.num_envs, P, self.params.num_obstacles, 2):
+            raise ValueError("scene pool shapes must be [N,P,2] and [N,P,num_obstacles,2]")
+        self._check(self._L.salp_set_scene_pool(self._h, _np_ptr(targets), _np_ptr(obstacles), P))
+
+    def reset(self, mask=None) -> np.ndarray:
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        if m is not None and m.shape != (self.num_envs,):
+            raise ValueError("mask must have shape [num_envs]")
+        if m is None:
+            self._check(self._L.salp_reset_host(self._h, None, _np_ptr(self.obs)))
+        else:
+            tmp = np.empty_like(self.obs)
+            self._check(self._L.salp_reset_host(self._h, _np_ptr(m), _np_ptr(tmp)))
+            sel = m.astype(bool)
+            self.obs[sel] = tmp[sel]
+        return self.obs
+
+    def step(self, actions, auto_reset: bool = False, sort_by_k: bool = False, extras: bool = True):
+        a = np.ascontiguousarray(actions, np.float32)
+        if a.shape != (self.num_envs, 3):
+            raise ValueError(f"actions must have shape [{self.num_envs}, 3]")
+        io = self._io_host
+        io.actions = a.ctypes.data
+        io.obs = self.obs.ctypes.data
+        io.reward = self.reward.ctypes.data
+        io.terminated = self.terminated.ctypes.data
+        io.truncated = self.truncated.ctypes.data
+        io.terminal_obs = self.terminal_obs.ctypes.data
+        io.reward_terms = self.terms.ctypes.data if extras else None
+        io.substeps = self.substeps.ctypes.data if extras else None
+        io.episode_metrics = self.metrics.ctypes.data if extras else None
+        flags = (STEP_AUTORESET if auto_reset else 0) | (STEP_SORT_BY_K if sort_by_k else 0)
+        self._check(self._L.salp_step_host(self._h, C.byref(io), flags))
+        return self.obs, self.reward, self.terminated, self.truncated
+
+    def get_state(self, name: str) -> np.ndarray:
+        out = np.zeros(self.num_envs, field_dtype(name))
+        self._check(self._L.salp_get_state(self._h, field_id(name), _np_ptr(out), 0, self.num_envs))
+        return out
+
+    def set_state(self, name: str, values):
+        v = np.ascontiguousarray(np.broadcast_to(values, (self.num_envs,)), field_dtype(name))
+        self._check(self._L.salp_set_state(self._h, field_id(name), _np_ptr(v), 0, self.num_envs))
+
+    # ------------------------------------------------------------------ device (torch) face
+    def _device_buffers(self):
+        if self._dev is None:
+            import torch
+            dev = torch.device("cuda", self.device)
+            n, d = self.num_envs, self.obs_dim
+            self._dev = dict(
+                obs=torch.zeros((n, d), dtype=torch.float32, device=dev),
+                terminal_obs=torch.zeros((n, d), dtype=torch.float32, device=dev),
+                reward=torch.zeros(n, dtype=torch.float32, device=dev),
+                terminated=torch.zeros(n, dtype=torch.uint8, device=dev),
+                truncated=torch.zeros(n, dtype=torch.uint8, device=dev),
+                substeps=torch.zeros(n, dtype=torch.int32, device=dev),
+                terms=torch.zeros((n, NUM_REWARD_TERMS), dtype=torch.float64, device=dev),
+                metrics=torch.zeros((n, NUM_EPISODE_METRICS), dtype=torch.float64, device=dev),
+            )
+            self._io_dev = _lib.SalpStepIO()
+        return self._dev
+
+    @staticmethod
+    def _stream_ptr(device: int):
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+    def reset_device(self, mask=None):
+        """mask: optional uint8/bool CUDA tensor [N].  Returns the obs tensor [N,D] (device)."""
+        import torch
+        bufs = self._device_buffers()
+        mptr = None
+        if mask is not None:
+            mask = mask.to(torch.uint8).contiguous()
+            mptr = C.c_void_p(mask.data_ptr())
+            tmp = torch.empty_like(bufs["obs"])
+            self._check(self._L.salp_reset(self._h, mptr, C.c_void_p(tmp.data_ptr()), self._stream_ptr(self.device)))
+            bufs["obs"] = torch.where(mask.bool()[:, None], tmp, bufs["obs"])
+        else:
+            self._check(self._L.salp_reset(self._h, None, C.c_void_p(bufs["obs"].data_ptr()),
+                                           self._stream_ptr(self.device)))
+        return bufs["obs"]
+
+    def step_device(self, actions, auto_reset: bool = True, sort_by_k: bool = False, extras: bool = False):
+        """actions: float32 CUDA tensor [N,3] on this batch's device.  Asynchronous on the current
+        torch stream.  Returns (obs, reward, terminated, truncated) device tensors (reused every
+        call); ``self.dev["terminal_obs"]`` etc. hold the rest."""
+        import torch
+        bufs = self._device_buffers()
+        if actions.dtype != torch.float32 or not actions.is_cuda or tuple(actions.shape) != (self.num_envs, 3):
+            raise ValueError("actions must be a float32 CUDA tensor of shape [num_envs, 3]")
+        actions = actions.contiguous()
+        io = self._io_dev
+        io.actions = actions.data_ptr()
+        io.obs = bufs["obs"].data_ptr()
+        io.reward = bufs["reward"].data_ptr()
+        io.terminated = bufs["terminated"].data_ptr()
+        io.truncated = bufs["truncated"].data_ptr()
+        io.terminal_obs = bufs["terminal_obs"].data_ptr()
+        io.substeps = bufs["substeps"].data_ptr()
+        io.reward_terms = bufs["terms"].data_ptr() if extras else None
+        io.episode_metrics = bufs["metrics"].data_ptr() if extras else None
+        flags = (STEP_AUTORESET if auto_reset else 0) | (STEP_SORT_BY_K if sort_by_k else 0)
+        self._check(self._L.salp_step(self._h, C.byref(io), flags, self._stream_ptr(self.device)))
+        return bufs["obs"], bufs["reward"], bufs["terminated"], bufs["truncated"]
+
+    @property
+    def dev(self):
+        return self._device_buffers()
+
+    def state_tensor(self, name: str):
+        """Zero-copy torch view of one state column (salp_state_ptr)."""
+        import torch
+        p = C.c_void_p()
+        self._check(self._L.salp_state_ptr(self._h, field_id(name), C.byref(p)))
+        dt = {np.float64: torch.float64, np.float32: torch.float32, np.int32: torch.int32}[field_dtype(name)]
+        iface = {"shape": (self.num_envs,), "typestr": np.dtype(field_dtype(name)).str,
+                 "data": (p.value, False), "version": 2}
+
+        class _Holder:
+            __cuda_array_interface__ = iface
+        t = torch.as_tensor(_Holder(), device=torch.device("cuda", self.device))
+        assert t.dtype == dt
+        t._salp_owner = self   # keep the handle alive as long as the view
+        return t

@@ -1,0 +1,131 @@
+// salp_common.cuh -- state layout and launch plumbing shared by the kernels and the C ABI.
+//
+// HBM layout (DESIGN.md "Data layout"): structure-of-arrays, one column per scalar, env index
+// fastest, so a warp's 32 loads of one column are one 128 B (f32/i32) or 256 B (f64) request.
+//   f64 columns: double [SALP_NUM_F64_FIELDS][N]
+//   f32 columns: float  [NUM_F32][N]
+//   i32 columns: int32  [NUM_I32][N]
+// The env-facing I/O arrays (actions [N,3], obs [N,D], ...) keep the row-major layout SB3 hands
+// over; they are ~100 B per env-step against ~3.5e5 flop, i.e. irrelevant to the roofline.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/salp_b200.h"
+
+#define SALP_MAX_SUBSTEPS 4096          // cycles longer than this raise SALP_ERR_RANGE (Box actions: K <= 1348)
+#define SALP_NUM_F32 (SALP_F32_END - SALP_F32_BASE)
+#define SALP_NUM_I32 (SALP_I32_END - SALP_I32_BASE)
+
+// Every per-env routine is `__host__ __device__` so that tests/emu/ can compile the very same
+// step body for the host and check its logic against the oracle in the GPU-less CI container.
+// The product library (libsalp_b200.so) only ever launches the __global__ kernels.
+#define SALP_HD __host__ __device__ __forceinline__
+
+struct SalpView {
+  double* f64;          // [SALP_NUM_F64_FIELDS][n]
+  float* f32;           // [SALP_NUM_F32][n]
+  int32_t* i32;         // [SALP_NUM_I32][n]
+  int64_t n;            // envs on this GPU
+  int64_t env_id_offset;
+  uint64_t seed;
+  // scene pool (nullable): targets [n,P,2], obstacles [n,P,nobs,2]
+  const float* pool_targets;
+  const float* pool_obstacles;
+  int64_t pool_P;
+  int32_t* status;      // sticky device status word (0 = ok)
+  const double* time_table;   // t_k, k = 0..SALP_MAX_SUBSTEPS: k-fold repeated `+= dt` (robot.py:674)
+};
+
+// Per-step scratch owned by the handle (K-sort path).
+struct SalpScratch {
+  int32_t* K;           // [n]   substep count of the pending cycle
+  int32_t* order;       // [n]   env indices sorted by K (descending)
+  int32_t* hist;        // [SALP_MAX_SUBSTEPS + 2] counting-sort histogram / offsets
+};
+
+// Launchers implemented in salp_kernels.cu (all asynchronous on `stream`).
+// Each returns the number of kernels it launched, or a negative SalpStatus.
+int salp_launch_reset(const SalpParams& p, const SalpView& v, const uint8_t* mask, float* obs,
+                      cudaStream_t stream);
+int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& io, uint32_t flags,
+                     const SalpScratch& scratch, cudaStream_t stream);
+int salp_launch_init(const SalpParams& p, const SalpView& v, cudaStream_t stream);
+
+// ---- rounding-exact scalar ops -------------------------------------------------------------
+// nvcc contracts a*b+c into an FMA in device code and the host compiler may keep x87/AVX
+// intermediates; wherever the reference's result depends on a *separately rounded* float32 or
+// float64 operation (SURVEY.md hard parts 1-2) the code says so with these.
+namespace rn {
+SALP_HD float fmul(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fmul_rn(a, b);
+#else
+  volatile float r = a * b; return r;
+#endif
+}
+SALP_HD float fadd(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fadd_rn(a, b);
+#else
+  volatile float r = a + b; return r;
+#endif
+}
+SALP_HD float fsub(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fsub_rn(a, b);
+#else
+  volatile float r = a - b; return r;
+#endif
+}
+SALP_HD float fdiv(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fdiv_rn(a, b);
+#else
+  volatile float r = a / b; return r;
+#endif
+}
+SALP_HD float fsqrt(float a) {
+#ifdef __CUDA_ARCH__
+  return __fsqrt_rn(a);
+#else
+  volatile float r = sqrtf(a); return r;
+#endif
+}
+SALP_HD float ffma(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+  return __fmaf_rn(a, b, c);
+#else
+  return fmaf(a, b, c);
+#endif
+}
+SALP_HD double dmul(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dmul_rn(a, b);
+#else
+  volatile double r = a * b; return r;
+#endif
+}
+SALP_HD double dadd(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dadd_rn(a, b);
+#else
+  volatile double r = a + b; return r;
+#endif
+}
+SALP_HD double dsub(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dsub_rn(a, b);
+#else
+  volatile double r = a - b; return r;
+#endif
+}
+SALP_HD double ddiv(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __ddiv_rn(a, b);
+#else
+  volatile double r = a / b; return r;
+#endif
+}
+}  // namespace rn

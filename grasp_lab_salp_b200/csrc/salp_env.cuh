@@ -1,0 +1,350 @@
+// salp_env.cuh -- the per-env step and reset bodies (SalpRobotEnv.step / reset, batched).
+//
+// One thread owns one env.  env_step() is the whole of salp_robot_env.py:196-299 for that env:
+// action rescale -> nozzle inverse kinematics -> Robot.set_control -> the K-substep breathing
+// cycle (run_cycle<PREC>, state in registers) -> reward, observation, collision, termination,
+// episode bookkeeping -> optional SB3-style auto-reset.  Reference citations are file:line in
+// Avielstein/GRASP_LAB_SALP src/.
+#pragma once
+#include "salp_loop_f64.cuh"
+#include "salp_loop_mixed.cuh"
+
+// column accessors (SoA, env index fastest)
+struct Cols {
+  const SalpView& v;
+  int64_t i;
+  SALP_HD double& d(int f) const { return v.f64[(int64_t)f * v.n + i]; }
+  SALP_HD float& f(int f) const { return v.f32[(int64_t)(f - SALP_F32_BASE) * v.n + i]; }
+  SALP_HD int32_t& n(int f) const { return v.i32[(int64_t)(f - SALP_I32_BASE) * v.n + i]; }
+};
+
+SALP_HD double norm2d(double x, double y) { return sqrt(x * x + y * y); }
+
+SALP_HD void raise_status(const SalpView& v, int code) {
+#ifdef __CUDA_ARCH__
+  atomicMin(v.status, code);
+#else
+  if (code < *v.status) *v.status = code;
+#endif
+}
+
+// _get_observation (salp_robot_env.py:651-670)
+SALP_HD void write_observation(const SalpParams& p, const Cols& c, const double pw[3],
+                               const double eul[3], const double v[3], double wz, float* obs) {
+  double tx = (double)c.f(SALP_F_TARGET_X), ty = (double)c.f(SALP_F_TARGET_Y);
+  Rot3 R = rotation_zyx(eul[0], eul[1], eul[2]);
+  double bx, by;
+  to_body_frame_xy(R, tx - pw[0], ty - pw[1], bx, by);
+  obs[0] = (float)bx;
+  obs[1] = (float)by;
+  obs[2] = (float)v[0];
+  obs[3] = (float)v[1];
+  obs[4] = (float)wz;
+  obs[5] = (float)atan2(by, bx);
+  for (int k = 0; k < p.num_obstacles; k++) {
+    obs[6 + 2 * k] = (float)((double)c.f(SALP_F_OBSTACLE0_X + 2 * k) - pw[0]);
+    obs[7 + 2 * k] = (float)((double)c.f(SALP_F_OBSTACLE0_X + 2 * k + 1) - pw[1]);
+  }
+}
+
+// generate_target_point("random") + _generate_obstacles (salp_robot_env.py:449-559), or the
+// caller's scene pool (salp_set_scene_pool) when one is installed.
+SALP_HD void sample_scene(const SalpParams& p, const SalpView& v, const Cols& c, int episode) {
+  const int nobs = p.num_obstacles;
+  if (v.pool_P > 0) {
+    int64_t s = (int64_t)episode % v.pool_P;
+    const float* t = v.pool_targets + (c.i * v.pool_P + s) * 2;
+    c.f(SALP_F_TARGET_X) = t[0];
+    c.f(SALP_F_TARGET_Y) = t[1];
+    const float* ob = v.pool_obstacles + (c.i * v.pool_P + s) * nobs * 2;
+    for (int k = 0; k < 2 * nobs; k++) c.f(SALP_F_OBSTACLE0_X + k) = ob[k];
+    return;
+  }
+  int64_t gid = v.env_id_offset + c.i;
+  int draw = 0;
+  float tx, ty;
+  sample_point(p, v.seed, gid, episode, draw++, tx, ty);
+  c.f(SALP_F_TARGET_X) = tx;
+  c.f(SALP_F_TARGET_Y) = ty;
+  const float min_clear = 0.5f;                                  // salp_robot_env.py:540-541
+  const float min_sep = (float)(2 * p.obstacle_radius + 0.1);    // :542
+  for (int k = 0; k < nobs; k++) {
+    float px = 0.f, py = 0.f;
+    for (int attempt = 0; attempt < 200; attempt++) {
+      sample_point(p, v.seed, gid, episode, draw++, px, py);
+      bool too_close = false;
+      for (int j = 0; j < k; j++)
+        too_close |= dist2f(px, py, c.f(SALP_F_OBSTACLE0_X + 2 * j), c.f(SALP_F_OBSTACLE0_X + 2 * j + 1)) < min_sep;
+      if (dist2f(px, py, 0.f, 0.f) > min_clear && dist2f(px, py, tx, ty) > min_clear && !too_close) break;
+      // after 200 rejections the reference silently places fewer obstacles (shorter obs); this
+      // restatement keeps the last candidate instead (probability ~1e-140)
+    }
+    c.f(SALP_F_OBSTACLE0_X + 2 * k) = px;
+    c.f(SALP_F_OBSTACLE0_X + 2 * k + 1) = py;
+  }
+}
+
+// Robot.__init__ + Nozzle.__init__ + make_env's set_angles(0, 0) (robot.py:20-47, 261-374;
+// train_robot.py:11-21): the state of an env that has never been reset.
+SALP_HD void env_init(const SalpParams& p, const SalpView& v, int64_t i) {
+  Cols c{v, i};
+  for (int f = 0; f < SALP_NUM_F64_FIELDS; f++) c.d(f) = 0.0;
+  for (int f = SALP_F32_BASE; f < SALP_F32_END; f++) c.f(f) = 0.f;
+  for (int f = SALP_I32_BASE; f < SALP_I32_END; f++) c.n(f) = 0;
+  c.n(SALP_F_PHASE) = 3;
+  double l = p.init_length, w = p.init_width;
+  c.d(SALP_F_LENGTH) = l;
+  c.d(SALP_F_WIDTH) = w;
+  double vol = ellipsoid_volume(l, w) - p.tube_volume;
+  c.d(SALP_F_PREV_VOLUME) = vol;
+  double I[3];
+  inertia_diag(l, w, p.nozzle_mass, I);
+  c.d(SALP_F_PREV_I_X) = I[0];
+  c.d(SALP_F_PREV_I_Y) = I[1];
+  c.d(SALP_F_PREV_I_Z) = I[2];
+  double com = center_of_mass_x(p, l, w, p.density * vol);
+  c.d(SALP_F_COM_X) = com;
+  c.d(SALP_F_PREV_COM_X) = com;
+}
+
+// SalpRobotEnv.reset (salp_robot_env.py:114-155) incl. Robot.reset (robot.py:452-501).
+// Works on the HBM columns directly (a reset is ~100 B of traffic and ~200 flop).
+SALP_HD void env_reset(const SalpParams& p, const SalpView& v, int64_t i, float* obs) {
+  Cols c{v, i};
+  int episode = c.n(SALP_F_EPISODE_INDEX);
+  sample_scene(p, v, c, episode);
+  c.n(SALP_F_EPISODE_INDEX) = episode + 1;
+  // Robot.reset: motion state to zero; the nozzle (angle1, angle2, yaw) is NOT touched
+  for (int f = SALP_F_VEL_X; f <= SALP_F_PREVANGLE_Z; f++) c.d(f) = 0.0;
+  c.d(SALP_F_SPEED_WORLD) = 0.0;
+  c.n(SALP_F_CYCLE) = 0;
+  c.n(SALP_F_PHASE) = 3;
+  // centre of mass is evaluated BEFORE length/width are restored (robot.py:478 vs :485-486)
+  {
+    double l = c.d(SALP_F_LENGTH), w = c.d(SALP_F_WIDTH);
+    double wm = p.density * (ellipsoid_volume(l, w) - p.tube_volume);
+    double com = center_of_mass_x(p, l, w, wm);
+    c.d(SALP_F_COM_X) = com;
+    c.d(SALP_F_PREV_COM_X) = com;
+    c.d(SALP_F_COM_RATE_X) = 0.0;        // (com - prev_com)/dt with prev_com == com
+    c.d(SALP_F_PREV_COM_RATE_X) = 0.0;
+    c.d(SALP_F_COM_ACC_X) = 0.0;
+  }
+  double l0 = p.init_length, w0 = p.init_width;
+  c.d(SALP_F_LENGTH) = l0;
+  c.d(SALP_F_WIDTH) = w0;
+  c.d(SALP_F_PREV_VOLUME) = ellipsoid_volume(l0, w0) - p.tube_volume;
+  double I[3];
+  inertia_diag(l0, w0, p.nozzle_mass, I);
+  c.d(SALP_F_PREV_I_X) = I[0];
+  c.d(SALP_F_PREV_I_Y) = I[1];
+  c.d(SALP_F_PREV_I_Z) = I[2];
+  // env part (salp_robot_env.py:127-153)
+  double tx = (double)c.f(SALP_F_TARGET_X), ty = (double)c.f(SALP_F_TARGET_Y);
+  double d0 = norm2d(0.0 - tx, 0.0 - ty);
+  c.d(SALP_F_PREV_DIST) = d0;
+  c.f(SALP_F_PREV_ACTION0) = 0.f;
+  c.f(SALP_F_PREV_ACTION1) = 0.f;
+  c.f(SALP_F_PREV_ACTION2) = 0.f;
+  c.n(SALP_F_EP_LENGTH) = 0;
+  for (int f = SALP_F_EP_RETURN; f <= SALP_F_EP_SUBSTEPS; f++) c.d(f) = 0.0;
+  c.d(SALP_F_EP_INITIAL_DISTANCE) = d0;
+  if (obs) {
+    const double z3[3] = {0.0, 0.0, 0.0};
+    write_observation(p, c, z3, z3, z3, 0.0, obs);
+  }
+}
+
+// _calculate_episode_metrics (salp_robot_env.py:399-447) + SB3 Monitor's r / l
+SALP_HD void write_episode_metrics(const Cols& c, double last_x, double last_y, double final_dist,
+                                   int ep_len, double* m) {
+  for (int k = 0; k < SALP_NUM_EPISODE_METRICS; k++) m[k] = 0.0;
+  double path = c.d(SALP_F_EP_PATH_LENGTH);
+  m[SALP_EM_RETURN] = c.d(SALP_F_EP_RETURN);
+  m[SALP_EM_LENGTH] = (double)ep_len;
+  m[SALP_EM_PATH_LENGTH] = path;
+  double direct = norm2d(last_x, last_y);
+  m[SALP_EM_DIRECT_DISTANCE] = direct;
+  m[SALP_EM_PATH_EFFICIENCY] = path > 0 ? direct / path : 0.0;
+  m[SALP_EM_FINAL_DISTANCE] = final_dist;
+  m[SALP_EM_INITIAL_DISTANCE] = c.d(SALP_F_EP_INITIAL_DISTANCE);
+  double n = (double)ep_len;
+  if (ep_len > 0) {
+    m[SALP_EM_AVG_COMPRESSION] = c.d(SALP_F_EP_SUM_A0) / n;
+    m[SALP_EM_AVG_COAST_TIME] = c.d(SALP_F_EP_SUM_A1) / n;
+    m[SALP_EM_AVG_NOZZLE_ANGLE] = c.d(SALP_F_EP_SUM_ABS_A2) / n;
+    for (int k = 0; k < 7; k++) m[SALP_EM_AVG_REWARD_TRACK + k] = c.d(SALP_F_EP_SUM_TERM0 + k) / n;
+  }
+  m[SALP_EM_AVG_VELOCITY] = c.d(SALP_F_EP_SUM_SPEED) / (n + 1.0);
+  m[SALP_EM_TOTAL_SUBSTEPS] = c.d(SALP_F_EP_SUBSTEPS);
+}
+
+SALP_HD void load_body(const Cols& c, Body64& b) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    b.v[k] = c.d(SALP_F_VEL_X + k);
+    b.w[k] = c.d(SALP_F_ANGVEL_X + k);
+    b.eul[k] = c.d(SALP_F_EULER_X + k);
+    b.pw[k] = c.d(SALP_F_POSW_X + k);
+    b.acc[k] = c.d(SALP_F_ACC_X + k);
+    b.alp[k] = c.d(SALP_F_ANGACC_X + k);
+    b.pos[k] = c.d(SALP_F_POS_X + k);
+    b.ang[k] = c.d(SALP_F_ANGLE_X + k);
+    b.prevI[k] = c.d(SALP_F_PREV_I_X + k);
+  }
+  b.phase = c.n(SALP_F_PHASE);
+  b.length = c.d(SALP_F_LENGTH);
+  b.width = c.d(SALP_F_WIDTH);
+  b.prev_volume = c.d(SALP_F_PREV_VOLUME);
+  b.com = c.d(SALP_F_COM_X);
+  b.prev_com = c.d(SALP_F_PREV_COM_X);
+  b.com_rate = c.d(SALP_F_COM_RATE_X);
+  b.prev_com_rate = c.d(SALP_F_PREV_COM_RATE_X);
+  b.com_acc = c.d(SALP_F_COM_ACC_X);
+  b.speed_world = c.d(SALP_F_SPEED_WORLD);
+}
+
+SALP_HD void store_body(const Cols& c, const Body64& b) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    c.d(SALP_F_VEL_X + k) = b.v[k];
+    c.d(SALP_F_ANGVEL_X + k) = b.w[k];
+    c.d(SALP_F_EULER_X + k) = b.eul[k];
+    c.d(SALP_F_POSW_X + k) = b.pw[k];
+    c.d(SALP_F_ACC_X + k) = b.acc[k];
+    c.d(SALP_F_ANGACC_X + k) = b.alp[k];
+    c.d(SALP_F_POS_X + k) = b.pos[k];
+    c.d(SALP_F_ANGLE_X + k) = b.ang[k];
+    c.d(SALP_F_PREV_I_X + k) = b.prevI[k];
+  }
+  c.n(SALP_F_PHASE) = b.phase;
+  c.d(SALP_F_LENGTH) = b.length;
+  c.d(SALP_F_WIDTH) = b.width;
+  c.d(SALP_F_PREV_VOLUME) = b.prev_volume;
+  c.d(SALP_F_COM_X) = b.com;
+  c.d(SALP_F_PREV_COM_X) = b.prev_com;
+  c.d(SALP_F_COM_RATE_X) = b.com_rate;
+  c.d(SALP_F_PREV_COM_RATE_X) = b.prev_com_rate;
+  c.d(SALP_F_COM_ACC_X) = b.com_acc;
+  c.d(SALP_F_SPEED_WORLD) = b.speed_world;
+}
+
+// SalpRobotEnv.step (salp_robot_env.py:196-299) for env i.
+template <int PREC>
+SALP_HD void env_step(const SalpParams& p, const SalpView& v, const SalpStepIO& io, uint32_t flags,
+                      int64_t i) {
+  Cols c{v, i};
+  const int D = SALP_OBS_BASE + 2 * p.num_obstacles;
+  const float a0 = io.actions[3 * i], a1 = io.actions[3 * i + 1], a2 = io.actions[3 * i + 2];
+
+  // :201-209  rescale, Nozzle.set_yaw_angle / solve_angles, Robot.set_control
+  CyclePlan plan = make_cycle_plan(p, a0, a1, a2, c.d(SALP_F_NOZZLE_ANGLE1), c.d(SALP_F_NOZZLE_ANGLE2));
+  c.f(SALP_F_NOZZLE_YAW) = plan.yaw32;
+  c.d(SALP_F_NOZZLE_ANGLE1) = plan.angle1;
+  c.d(SALP_F_NOZZLE_ANGLE2) = plan.angle2;
+  const int cycle = c.n(SALP_F_CYCLE) + 1;
+  c.n(SALP_F_CYCLE) = cycle;
+
+  // :210  Robot.step_through_cycle (robot.py:740-757)
+  Body64 b;
+  load_body(c, b);
+  const double tot = plan.total64;
+  // lag-by-one: displacement of the PREVIOUS cycle over the NEW total (robot.py:744-748)
+  const double avg_vy = (b.pos[1] - c.d(SALP_F_PREVPOS_Y)) / tot;
+  const double avg_wz = (b.ang[2] - c.d(SALP_F_PREVANGLE_Z)) / tot;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    c.d(SALP_F_PREVPOS_X + k) = b.pos[k];
+    c.d(SALP_F_PREVANGLE_X + k) = b.ang[k];
+  }
+  const double last_x = b.pw[0], last_y = b.pw[1];     // episode_positions[-1]
+  double t = 0.0;
+  const int K = run_cycle<PREC>(p, plan, v.time_table, b, t);
+  if (K < 0) raise_status(v, SALP_ERR_RANGE);
+  store_body(c, b);
+
+  // :238-243
+  const double path = c.d(SALP_F_EP_PATH_LENGTH) + norm2d(b.pw[0] - last_x, b.pw[1] - last_y);
+  c.d(SALP_F_EP_PATH_LENGTH) = path;
+  c.d(SALP_F_EP_SUM_SPEED) += b.speed_world;
+  const double tx = (double)c.f(SALP_F_TARGET_X), ty = (double)c.f(SALP_F_TARGET_Y);
+  const double dx = b.pw[0] - tx, dy = b.pw[1] - ty;
+  const double dist = norm2d(dx, dy);
+
+  // :246  _calculate_reward_with_components (:349-397)
+  double terms[7];
+  terms[0] = (-dist + c.d(SALP_F_PREV_DIST)) * 100;
+  c.d(SALP_F_PREV_DIST) = dist;
+  Rot3 R = rotation_zyx(b.eul[0], b.eul[1], b.eul[2]);
+  double bx, by;
+  to_body_frame_xy(R, dx, dy, bx, by);
+  terms[1] = -0.5 * fabs(atan2(-by, -bx));
+  const int ep_len = c.n(SALP_F_EP_LENGTH);
+  if (ep_len == 0) {
+    // first step of an episode: prev_action is reset()'s float64 zeros (:128) -> float64 arithmetic
+    double ch = (double)a2 - 0.0;
+    terms[2] = -1.0 * (ch * ch);
+  } else {
+    float ch = rn::fsub(a2, c.f(SALP_F_PREV_ACTION2));
+    terms[2] = (double)rn::fmul(-1.0f, rn::fmul(ch, ch));
+  }
+  terms[3] = -10.0 * fabs(avg_wz);
+  terms[4] = -0.1;
+  terms[5] = -100.0 * fabs(avg_vy);
+  terms[6] = 0.0;
+  // :255 _check_obstacle_collision (:561-568) shares the distances with the proximity penalty
+  const double cur_len = p.init_length - shape_delta(b.phase, t, plan.refill, plan.T0, (double)plan.contraction32,
+                                                     plan.contract_rate, plan.release_rate);
+  bool hit = false;
+  if (p.num_obstacles > 0) {
+    double min_dist = INFINITY;
+    for (int k = 0; k < p.num_obstacles; k++) {
+      double d = norm2d(b.pw[0] - (double)c.f(SALP_F_OBSTACLE0_X + 2 * k),
+                        b.pw[1] - (double)c.f(SALP_F_OBSTACLE0_X + 2 * k + 1));
+      min_dist = d < min_dist ? d : min_dist;
+      hit |= d < p.obstacle_radius + cur_len / 2;
+    }
+    const double danger = 2.0 * p.obstacle_radius;
+    if (min_dist < danger) terms[6] = -1.0 * (1.0 - min_dist / danger);
+  }
+  double rew = terms[0] + terms[1] + terms[2] + terms[3] + terms[4] + terms[5] + terms[6];
+
+  // :250  observation
+  float* obs = io.obs + i * D;
+  write_observation(p, c, b.pw, b.eul, b.v, b.w[2], obs);
+
+  // :258-276  termination (cumulative, not exclusive)
+  bool done = false, trunc = false;
+  if (dist < p.target_radius) { done = true; rew += p.success_bonus; }
+  else if (dist > p.out_of_bounds_distance) { trunc = true; rew -= p.out_of_bounds_penalty; }
+  if (hit) { trunc = true; rew -= p.collision_penalty; }
+  if (cycle >= p.max_cycles) { trunc = true; rew -= p.timeout_penalty; }
+
+  // episode bookkeeping (:199, :247-248, Monitor)
+  c.n(SALP_F_EP_LENGTH) = ep_len + 1;
+  c.d(SALP_F_EP_SUM_A0) += (double)a0;
+  c.d(SALP_F_EP_SUM_A1) += (double)a1;
+  c.d(SALP_F_EP_SUM_ABS_A2) += fabs((double)a2);
+  for (int k = 0; k < 7; k++) c.d(SALP_F_EP_SUM_TERM0 + k) += terms[k];
+  c.d(SALP_F_EP_RETURN) += rew;
+  c.d(SALP_F_EP_SUBSTEPS) += (double)(K < 0 ? SALP_MAX_SUBSTEPS : K);
+  c.f(SALP_F_PREV_ACTION0) = a0;
+  c.f(SALP_F_PREV_ACTION1) = a1;
+  c.f(SALP_F_PREV_ACTION2) = a2;
+
+  const bool ended = done || trunc;
+  if (io.episode_metrics && ended)
+    write_episode_metrics(c, b.pw[0], b.pw[1], dist, ep_len + 1, io.episode_metrics + i * SALP_NUM_EPISODE_METRICS);
+  io.reward[i] = (float)rew;
+  io.terminated[i] = done ? 1 : 0;
+  io.truncated[i] = trunc ? 1 : 0;
+  if (io.reward_terms) {
+    for (int k = 0; k < 7; k++) io.reward_terms[8 * i + k] = terms[k];
+    io.reward_terms[8 * i + 7] = rew;
+  }
+  if (io.substeps) io.substeps[i] = K < 0 ? SALP_MAX_SUBSTEPS : K;
+  if (io.terminal_obs)
+    for (int k = 0; k < D; k++) io.terminal_obs[i * D + k] = obs[k];
+  // SB3 VecEnv worker semantics: reset the finished env, hand back the post-reset observation
+  if ((flags & SALP_STEP_AUTORESET) && ended) env_reset(p, v, i, obs);
+}

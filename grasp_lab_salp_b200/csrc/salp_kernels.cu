@@ -1,0 +1,118 @@
+// salp_kernels.cu -- __global__ kernels and their launchers (sm_100a).
+//
+// One thread per environment, state columns in HBM (SoA, coalesced), the whole breathing cycle
+// of an env in registers.  Kernel arguments (SalpParams, SalpView, SalpStepIO) are
+// __grid_constant__: they sit in the constant bank and every access is a uniform c[][] operand.
+#include "salp_step_kernel.cuh"
+
+__global__ void salp_init_kernel(const __grid_constant__ SalpParams p, const __grid_constant__ SalpView v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < v.n) env_init(p, v, i);
+}
+
+__global__ void salp_reset_kernel(const __grid_constant__ SalpParams p, const __grid_constant__ SalpView v,
+                                  const uint8_t* __restrict__ mask, float* __restrict__ obs) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n) return;
+  if (mask && !mask[i]) return;
+  const int D = SALP_OBS_BASE + 2 * p.num_obstacles;
+  env_reset(p, v, i, obs ? obs + i * D : nullptr);
+}
+
+// ---- K-sort: balance warps by substep count (SURVEY.md hard part 3) ----------------------------
+// salp_plan_kernel recomputes the cycle plan of every env (cheap: one inverse-kinematics solve)
+// and histograms K; salp_scan_kernel turns the histogram into descending-K offsets;
+// salp_scatter_kernel writes the env permutation.  The step kernel then walks `order`.
+__global__ void salp_plan_kernel(const __grid_constant__ SalpParams p, const __grid_constant__ SalpView v,
+                                 const float* __restrict__ actions, int32_t* __restrict__ Kout,
+                                 int32_t* __restrict__ hist) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n) return;
+  Cols c{v, i};
+  CyclePlan plan = make_cycle_plan(p, actions[3 * i], actions[3 * i + 1], actions[3 * i + 2],
+                                   c.d(SALP_F_NOZZLE_ANGLE1), c.d(SALP_F_NOZZLE_ANGLE2));
+  int K = plan_substeps(plan, v.time_table);
+  K = K < 0 ? SALP_MAX_SUBSTEPS : K;
+  Kout[i] = K;
+  atomicAdd(&hist[K], 1);
+}
+
+// one block of 1024 threads; bins 0..SALP_MAX_SUBSTEPS; offsets for DESCENDING K (long cycles first)
+__global__ void salp_scan_kernel(int32_t* __restrict__ hist) {
+  __shared__ int32_t part[1024];
+  constexpr int NB = SALP_MAX_SUBSTEPS + 1;
+  constexpr int PER = (NB + 1023) / 1024;
+  int tid = threadIdx.x;
+  int32_t local[PER];
+  int32_t sum = 0;
+#pragma unroll
+  for (int j = 0; j < PER; j++) {
+    int bin = NB - 1 - (tid * PER + j);          // reversed: thread 0 owns the largest K
+    int32_t h = bin >= 0 ? hist[bin] : 0;
+    local[j] = sum;
+    sum += h;
+  }
+  part[tid] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    int32_t x = tid >= off ? part[tid - off] : 0;
+    __syncthreads();
+    part[tid] += x;
+    __syncthreads();
+  }
+  int32_t base = tid ? part[tid - 1] : 0;
+#pragma unroll
+  for (int j = 0; j < PER; j++) {
+    int bin = NB - 1 - (tid * PER + j);
+    if (bin >= 0) hist[bin] = base + local[j];
+  }
+}
+
+__global__ void salp_scatter_kernel(int64_t n, const int32_t* __restrict__ K, int32_t* __restrict__ offsets,
+                                    int32_t* __restrict__ order) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t slot = atomicAdd(&offsets[K[i]], 1);
+  order[slot] = (int32_t)i;
+}
+
+#define SALP_LAUNCH_CHECK()                                  \
+  do {                                                       \
+    if (cudaPeekAtLastError() != cudaSuccess) return SALP_ERR_CUDA; \
+  } while (0)
+
+int salp_launch_init(const SalpParams& p, const SalpView& v, cudaStream_t stream) {
+  salp_init_kernel<<<grid_for(v.n, 128), 128, 0, stream>>>(p, v);
+  SALP_LAUNCH_CHECK();
+  return 1;
+}
+
+int salp_launch_reset(const SalpParams& p, const SalpView& v, const uint8_t* mask, float* obs,
+                      cudaStream_t stream) {
+  salp_reset_kernel<<<grid_for(v.n, 128), 128, 0, stream>>>(p, v, mask, obs);
+  SALP_LAUNCH_CHECK();
+  return 1;
+}
+
+int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& io, uint32_t flags,
+                     const SalpScratch& scratch, cudaStream_t stream) {
+  int launches = 0;
+  const int32_t* order = nullptr;
+  if (flags & SALP_STEP_SORT_BY_K) {
+    if (cudaMemsetAsync(scratch.hist, 0, sizeof(int32_t) * (SALP_MAX_SUBSTEPS + 2), stream) != cudaSuccess)
+      return SALP_ERR_CUDA;
+    salp_plan_kernel<<<grid_for(v.n, 128), 128, 0, stream>>>(p, v, io.actions, scratch.K, scratch.hist);
+    salp_scan_kernel<<<1, 1024, 0, stream>>>(scratch.hist);
+    salp_scatter_kernel<<<grid_for(v.n, 256), 256, 0, stream>>>(v.n, scratch.K, scratch.hist, scratch.order);
+    SALP_LAUNCH_CHECK();
+    launches += 3;
+    order = scratch.order;
+  }
+  const int block = block_for(v.n);
+  if (p.precision == SALP_PRECISION_F64)
+    salp_launch_step_f64(p, v, io, flags, order, stream);     // salp_step_f64.cu (compiled with -fmad=false)
+  else
+    salp_step_kernel<SALP_PRECISION_MIXED><<<grid_for(v.n, block), block, 0, stream>>>(p, v, io, flags, order);
+  SALP_LAUNCH_CHECK();
+  return launches + 1;
+}

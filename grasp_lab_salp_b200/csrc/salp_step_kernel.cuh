@@ -1,0 +1,25 @@
+// salp_step_kernel.cuh -- the step kernel template, shared by salp_kernels.cu (MIXED) and
+// salp_step_f64.cu (F64; that translation unit is compiled with -fmad=false so that the
+// reference-mode arithmetic is not contracted into FMAs the reference does not perform).
+#pragma once
+#include "salp_env.cuh"
+
+template <int PREC>
+__global__ void __launch_bounds__(128)
+salp_step_kernel(const __grid_constant__ SalpParams p, const __grid_constant__ SalpView v,
+                 const __grid_constant__ SalpStepIO io, uint32_t flags, const int32_t* __restrict__ order) {
+  int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= v.n) return;
+  int64_t i = order ? (int64_t)order[tid] : tid;
+  env_step<PREC>(p, v, io, flags, i);
+}
+
+static inline int block_for(int64_t n) {
+  // small batches: one warp per block so that the warps spread over all 148 SMs
+  return n <= 148 * 4 * 32 ? 32 : 128;
+}
+static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+
+void salp_launch_step_f64(const SalpParams& p, const SalpView& v, const SalpStepIO& io, uint32_t flags,
+                          const int32_t* order, cudaStream_t stream);

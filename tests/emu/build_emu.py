@@ -1,0 +1,41 @@
+"""TEST INFRASTRUCTURE ONLY: host build of the device step body (see salp_emu.cu)."""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+OUT = os.path.join(HERE, "_build")
+LIB = os.path.join(OUT, "libsalp_emu.so")
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "grasp_lab_salp_b200", "csrc")
+    files = [os.path.join(csrc, f) for f in sorted(os.listdir(csrc)) if f.endswith(".cuh")]
+    files += [os.path.join(HERE, "salp_emu.cu"), os.path.join(ROOT, "include", "salp_b200.h"), __file__]
+    for f in files:
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def build() -> str:
+    os.makedirs(OUT, exist_ok=True)
+    stamp = os.path.join(OUT, "emu.hash")
+    d = _digest()
+    if os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == d:
+        return LIB
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    # host code is what runs; the (unused) device pass still needs an arch.  No contraction on the
+    # host so that fp32/fp64 products and sums round separately, like the oracle build.
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-shared",
+           "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-mfma", "-o", LIB,
+           os.path.join(HERE, "salp_emu.cu")]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    with open(stamp, "w") as f:
+        f.write(d)
+    return LIB
