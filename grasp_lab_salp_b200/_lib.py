@@ -50,6 +50,7 @@ PROTOTYPES = {
     "salp_state_ptr": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
     "salp_check": (C.c_int, [C.c_void_p]),
     "salp_launch_count": (C.c_int64, [C.c_void_p]),
+    "salp_probe_fp32_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
 }
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsalp_b200.so")

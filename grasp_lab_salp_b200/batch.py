@@ -44,17 +44,36 @@ class SalpBatch:
             raise _lib.SalpError(rc, (self._L.salp_last_error(None) or b"").decode())
         self._h = h
         n, d = self.num_envs, self.obs_dim
-        # persistent host buffers of the numpy face
-        self.obs = np.zeros((n, d), np.float32)
-        self.terminal_obs = np.zeros((n, d), np.float32)
-        self.reward = np.zeros(n, np.float32)
-        self.terminated = np.zeros(n, np.uint8)
-        self.truncated = np.zeros(n, np.uint8)
-        self.terms = np.zeros((n, NUM_REWARD_TERMS), np.float64)
-        self.substeps = np.zeros(n, np.int32)
-        self.metrics = np.zeros((n, NUM_EPISODE_METRICS), np.float64)
+        # persistent host buffers of the numpy face (page-locked when torch can provide them, so
+        # the D2H copies of salp_step_host are true async DMA)
+        self._pinned = []
+        self.obs = self.host_buffer((n, d), np.float32)
+        self.terminal_obs = self.host_buffer((n, d), np.float32)
+        self.reward = self.host_buffer((n,), np.float32)
+        self.terminated = self.host_buffer((n,), np.uint8)
+        self.truncated = self.host_buffer((n,), np.uint8)
+        self.terms = self.host_buffer((n, NUM_REWARD_TERMS), np.float64)
+        self.substeps = self.host_buffer((n,), np.int32)
+        self.metrics = self.host_buffer((n, NUM_EPISODE_METRICS), np.float64)
         self._io_host = _lib.SalpStepIO()
         self._dev = None          # lazily created torch output tensors of the device face
+
+    def host_buffer(self, shape, dtype) -> np.ndarray:
+        """Zero-filled host array, page-locked if possible (callers can use it for actions too)."""
+        if self._cdll_is_cuda():
+            try:
+                import torch
+                tdt = {np.float32: torch.float32, np.float64: torch.float64, np.uint8: torch.uint8,
+                       np.int32: torch.int32}[np.dtype(dtype).type]
+                t = torch.zeros(tuple(shape), dtype=tdt).pin_memory()
+                self._pinned.append(t)
+                return t.numpy()
+            except Exception:
+                pass
+        return np.zeros(shape, dtype)
+
+    def _cdll_is_cuda(self) -> bool:
+        return b"sm_100a" in (self._L.salp_build_info() or b"")
 
     # ------------------------------------------------------------------ lifetime / errors
     def close(self):

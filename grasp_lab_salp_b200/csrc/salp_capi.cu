@@ -414,4 +414,41 @@ int salp_check(salp_handle h) {
   return SALP_OK;
 }
 
+int salp_probe_fp32_peak(int device, int millis, double* tflops_out) {
+  if (!tflops_out || millis <= 0) return SALP_ERR_INVALID;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return SALP_ERR_NO_DEVICE;
+  DeviceGuard g(device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SALP_ERR_CUDA;
+  float* scratch = nullptr;
+  cudaEvent_t e0, e1;
+  if (cudaMalloc((void**)&scratch, 4) != cudaSuccess) return SALP_ERR_ALLOC;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int blocks = prop.multiProcessorCount * 8;      // 2048 resident threads per SM
+  const int iters = 4096;
+  const double flop_per_launch = 2.0 * 8 * 16 * (double)iters * 256.0 * blocks;
+  double best = 0.0, spent = 0.0;
+  int rc = SALP_OK;
+  for (int rep = 0; rep < 1000 && spent < millis; rep++) {
+    cudaEventRecord(e0, 0);
+    if (salp_launch_ffma_probe(scratch, blocks, iters, 0) < 0) { rc = SALP_ERR_CUDA; break; }
+    cudaEventRecord(e1, 0);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { rc = SALP_ERR_CUDA; break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    spent += ms;
+    if (rep >= 2 && ms > 0) {                            // sustained: the LAST launches decide
+      double tf = flop_per_launch / (ms * 1e-3) / 1e12;
+      best = tf;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(scratch);
+  *tflops_out = best;
+  return rc;
+}
+
 }  // extern "C"

@@ -52,6 +52,7 @@ int salp_launch_reset(const SalpParams& p, const SalpView& v, const uint8_t* mas
 int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& io, uint32_t flags,
                      const SalpScratch& scratch, cudaStream_t stream);
 int salp_launch_init(const SalpParams& p, const SalpView& v, cudaStream_t stream);
+int salp_launch_ffma_probe(float* scratch, int blocks, int iters, cudaStream_t stream);
 
 // ---- rounding-exact scalar ops -------------------------------------------------------------
 // nvcc contracts a*b+c into an FMA in device code and the host compiler may keep x87/AVX

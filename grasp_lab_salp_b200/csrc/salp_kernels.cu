@@ -116,3 +116,23 @@ int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& i
   SALP_LAUNCH_CHECK();
   return launches + 1;
 }
+
+// ---- FP32 pipe probe (roofline denominator) -------------------------------------
+__global__ void __launch_bounds__(256) salp_ffma_probe_kernel(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 12345.678f) out[0] = s;     // never true; keeps the chains alive
+}
+
+int salp_launch_ffma_probe(float* scratch, int blocks, int iters, cudaStream_t stream) {
+  salp_ffma_probe_kernel<<<blocks, 256, 0, stream>>>(scratch, iters, 0.999f, 0.001f);
+  SALP_LAUNCH_CHECK();
+  return 1;
+}

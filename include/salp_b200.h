@@ -234,6 +234,12 @@ int salp_check(salp_handle h);
 /* Kernel launches issued by this handle so far (bench.py reports it as gpu_launches). */
 int64_t salp_launch_count(salp_handle h);
 
+/* Measurement tooling (no reference counterpart): register-resident FFMA micro-benchmark on
+ * `device`; writes the sustained FP32 rate in TFLOP/s (2 flop per FMA) over ~`millis` ms.
+ * bench.py uses it as the denominator of the FP32-pipe roofline (MEASURED_PEAKS.json has no
+ * FP32 SIMT figure). */
+int salp_probe_fp32_peak(int device, int millis, double* tflops_out);
+
 #ifdef __cplusplus
 }
 #endif
