@@ -216,11 +216,22 @@ def lockstep_compare(product, oracle, actions, *, resync, rtol, floor, reward_fl
             ok = np.isfinite(ref)
             e = rel_err(got[ok], ref[ok], floor)
             errs[col] = float(e.max()) if e.size else 0.0
-        ok = np.isfinite(rew_o)
-        errs["reward"] = float(rel_err(rew_p[ok], rew_o[ok], reward_floor).max()) if ok.any() else 0.0
-        ok = np.isfinite(obs_o)
-        errs["obs"] = float(rel_err(product.terminal_obs[ok], oracle.terminal_obs[ok], obs_floor).max())
-        errs["obs_after_reset"] = float(rel_err(obs_p[ok], obs_o[ok], obs_floor).max())
+        rew_o64, rew_p64 = oracle.terms[:, 7], product.terms[:, 7]      # float64 totals (io.reward is float32)
+        ok = np.isfinite(rew_o64)
+        errs["reward"] = float(rel_err(rew_p64[ok], rew_o64[ok], reward_floor).max()) if ok.any() else 0.0
+        np.testing.assert_allclose(rew_p[ok], rew_o64[ok].astype(np.float32), rtol=1e-5, atol=rtol * reward_floor * 10)
+        # observations: obs[5] = atan2(d_body.y, d_body.x) amplifies a position error by 1/distance
+        # (terminal observations are taken INSIDE the 0.2 m target radius), so it is compared as an
+        # arc length: |d heading| * distance; everything else directly
+        tob_p, tob_o = product.terminal_obs.astype(np.float64), oracle.terminal_obs.astype(np.float64)
+        lin = [j for j in range(tob_o.shape[1]) if j != 5]
+        ok = np.isfinite(tob_o).all(axis=1)
+        errs["obs"] = float(rel_err(tob_p[ok][:, lin], tob_o[ok][:, lin], obs_floor).max())
+        dist = np.hypot(tob_o[ok][:, 0], tob_o[ok][:, 1])
+        dh = np.abs((tob_p[ok][:, 5] - tob_o[ok][:, 5] + np.pi) % (2 * np.pi) - np.pi)
+        errs["obs_heading_arc"] = float((dh * np.minimum(dist, 1.0)).max() / obs_floor)
+        ok2 = np.isfinite(obs_o).all(axis=1)
+        errs["obs_after_reset"] = float(rel_err(obs_p[ok2][:, lin], obs_o[ok2][:, lin], obs_floor).max())
         history.append(errs)
         for k, v in errs.items():
             worst[k] = max(worst.get(k, 0.0), v)
