@@ -231,8 +231,8 @@ SALP_HD void store_body(const Cols& c, const Body64& b) {
 
 // SalpRobotEnv.step (salp_robot_env.py:196-299) for env i.
 template <int PREC>
-SALP_HD void env_step(const SalpParams& p, const SalpView& v, const SalpStepIO& io, uint32_t flags,
-                      int64_t i) {
+SALP_HD void env_step(const SalpParams& p, const SalpDerived& dv, const SalpView& v, const SalpStepIO& io,
+                      uint32_t flags, int64_t i) {
   Cols c{v, i};
   const int D = SALP_OBS_BASE + 2 * p.num_obstacles;
   const float a0 = io.actions[3 * i], a1 = io.actions[3 * i + 1], a2 = io.actions[3 * i + 2];
@@ -259,7 +259,7 @@ SALP_HD void env_step(const SalpParams& p, const SalpView& v, const SalpStepIO& 
   }
   const double last_x = b.pw[0], last_y = b.pw[1];     // episode_positions[-1]
   double t = 0.0;
-  const int K = run_cycle<PREC>(p, plan, v.time_table, b, t);
+  const int K = run_cycle<PREC>(p, dv, plan, v.time_table, b, t);
   if (K < 0) raise_status(v, SALP_ERR_RANGE);
   store_body(c, b);
 

@@ -112,7 +112,7 @@ int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& i
   if (p.precision == SALP_PRECISION_F64)
     salp_launch_step_f64(p, v, io, flags, order, stream);     // salp_step_f64.cu (compiled with -fmad=false)
   else
-    salp_step_kernel<SALP_PRECISION_MIXED><<<grid_for(v.n, block), block, 0, stream>>>(p, v, io, flags, order);
+    salp_step_kernel<SALP_PRECISION_MIXED><<<grid_for(v.n, block), block, 0, stream>>>(p, make_derived(p), v, io, flags, order);
   SALP_LAUNCH_CHECK();
   return launches + 1;
 }

@@ -155,13 +155,16 @@ SALP_DEV void substep_f64(const SalpParams& p, const CyclePlan& c, Body64& b, do
 
 // Robot.step_through_cycle's loop (robot.py:756-757).  Returns K, or -1 if the cycle would run
 // past SALP_MAX_SUBSTEPS (impossible for Box actions; guards against non-finite actions).
+struct SalpDerived;   // host-derived constants of the mixed loop (salp_loop_mixed.cuh); unused here
 template <int PREC>
-SALP_HD int run_cycle(const SalpParams& p, const CyclePlan& c, const double* time_table, Body64& b, double& t);
+SALP_HD int run_cycle(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c, const double* time_table,
+                      Body64& b, double& t);
 
 template <>
-SALP_HD int run_cycle<SALP_PRECISION_F64>(const SalpParams& p, const CyclePlan& c, const double* time_table,
-                                          Body64& b, double& t) {
+SALP_HD int run_cycle<SALP_PRECISION_F64>(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c,
+                                          const double* time_table, Body64& b, double& t) {
   (void)time_table;
+  (void)dv;
   refresh_shape_f64(p, b);
   b.mass_rate = (b.water_mass - b.prev_volume * p.density) / p.dt;
   t = 0.0;

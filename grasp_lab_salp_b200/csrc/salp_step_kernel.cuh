@@ -5,13 +5,14 @@
 #include "salp_env.cuh"
 
 template <int PREC>
-__global__ void __launch_bounds__(128)
-salp_step_kernel(const __grid_constant__ SalpParams p, const __grid_constant__ SalpView v,
-                 const __grid_constant__ SalpStepIO io, uint32_t flags, const int32_t* __restrict__ order) {
+__global__ void __launch_bounds__(128, 4)
+salp_step_kernel(const __grid_constant__ SalpParams p, const __grid_constant__ SalpDerived dv,
+                 const __grid_constant__ SalpView v, const __grid_constant__ SalpStepIO io, uint32_t flags,
+                 const int32_t* __restrict__ order) {
   int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= v.n) return;
   int64_t i = order ? (int64_t)order[tid] : tid;
-  env_step<PREC>(p, v, io, flags, i);
+  env_step<PREC>(p, dv, v, io, flags, i);
 }
 
 static inline int block_for(int64_t n) {

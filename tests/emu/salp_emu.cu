@@ -77,11 +77,12 @@ int salp_reset_host(salp_handle h, const uint8_t* mask, float* obs) {
 int salp_step_host(salp_handle h, const SalpStepIO* io, uint32_t flags) {
   if (!h || !io || !io->actions || !io->obs || !io->reward || !io->terminated || !io->truncated)
     return SALP_ERR_INVALID;
+  const SalpDerived dv = make_derived(h->params);
   for (int64_t i = 0; i < h->view.n; i++) {
     if (h->params.precision == SALP_PRECISION_F64)
-      env_step<SALP_PRECISION_F64>(h->params, h->view, *io, flags, i);
+      env_step<SALP_PRECISION_F64>(h->params, dv, h->view, *io, flags, i);
     else
-      env_step<SALP_PRECISION_MIXED>(h->params, h->view, *io, flags, i);
+      env_step<SALP_PRECISION_MIXED>(h->params, dv, h->view, *io, flags, i);
   }
   h->steps++;
   return SALP_OK;

@@ -173,6 +173,33 @@ PER_STEP_CHANNELS = ["posw_x", "posw_y", "vel_x", "vel_y", "euler_z", "angvel_z"
                      "prev_volume", "com_x", "prev_dist"]
 
 
+def obs_errors(got, ref, floor, tag):
+    """Observation error metrics (salp_robot_env.py:651-670 layout).  The body-frame target vector
+    obs[0:2] and each obstacle vector are compared as VECTORS (|d| / max(|ref vec|, floor)): a yaw
+    error rotates the vector, which is a large relative error on whichever component happens to
+    be small.  obs[5] = atan2(d_body.y, d_body.x) amplifies a position error by 1/distance
+    (terminal observations are taken inside the 0.2 m target radius), so it is compared as an arc
+    length |d heading| * min(distance, 1) against a 1 rad scale.  obs[2:5] (v_x, v_y, w_z) directly."""
+    got = np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    ok = np.isfinite(ref).all(axis=1)
+    got, ref = got[ok], ref[ok]
+    out = {}
+    if not len(ref):
+        return {tag: 0.0}
+    worst = 0.0
+    for a in [0] + list(range(6, ref.shape[1], 2)):
+        d = np.hypot(got[:, a] - ref[:, a], got[:, a + 1] - ref[:, a + 1])
+        nrm = np.hypot(ref[:, a], ref[:, a + 1])
+        worst = max(worst, float((d / np.maximum(nrm, floor)).max()))
+    worst = max(worst, float(rel_err(got[:, 2:5], ref[:, 2:5], floor).max()))
+    out[tag] = worst
+    dist = np.hypot(ref[:, 0], ref[:, 1])
+    dh = np.abs((got[:, 5] - ref[:, 5] + np.pi) % (2 * np.pi) - np.pi)
+    out[tag + "_heading_arc"] = float((dh * np.minimum(dist, 1.0)).max())
+    return out
+
+
 def lockstep_compare(product, oracle, actions, *, resync, rtol, floor, reward_floor=10.0, obs_floor=0.1,
                      num_obstacles=2, report=None):
     """Step `product` and `oracle` with the same actions [T,N,3] (auto-reset on, same scenes).
@@ -220,18 +247,8 @@ def lockstep_compare(product, oracle, actions, *, resync, rtol, floor, reward_fl
         ok = np.isfinite(rew_o64)
         errs["reward"] = float(rel_err(rew_p64[ok], rew_o64[ok], reward_floor).max()) if ok.any() else 0.0
         np.testing.assert_allclose(rew_p[ok], rew_o64[ok].astype(np.float32), rtol=1e-5, atol=rtol * reward_floor * 10)
-        # observations: obs[5] = atan2(d_body.y, d_body.x) amplifies a position error by 1/distance
-        # (terminal observations are taken INSIDE the 0.2 m target radius), so it is compared as an
-        # arc length: |d heading| * distance; everything else directly
-        tob_p, tob_o = product.terminal_obs.astype(np.float64), oracle.terminal_obs.astype(np.float64)
-        lin = [j for j in range(tob_o.shape[1]) if j != 5]
-        ok = np.isfinite(tob_o).all(axis=1)
-        errs["obs"] = float(rel_err(tob_p[ok][:, lin], tob_o[ok][:, lin], obs_floor).max())
-        dist = np.hypot(tob_o[ok][:, 0], tob_o[ok][:, 1])
-        dh = np.abs((tob_p[ok][:, 5] - tob_o[ok][:, 5] + np.pi) % (2 * np.pi) - np.pi)
-        errs["obs_heading_arc"] = float((dh * np.minimum(dist, 1.0)).max() / obs_floor)
-        ok2 = np.isfinite(obs_o).all(axis=1)
-        errs["obs_after_reset"] = float(rel_err(obs_p[ok2][:, lin], obs_o[ok2][:, lin], obs_floor).max())
+        errs.update(obs_errors(product.terminal_obs, oracle.terminal_obs, obs_floor, "obs"))
+        errs.update(obs_errors(obs_p, obs_o, obs_floor, "obs_after_reset"))
         history.append(errs)
         for k, v in errs.items():
             worst[k] = max(worst.get(k, 0.0), v)
