@@ -201,7 +201,7 @@ def obs_errors(got, ref, floor, tag):
 
 
 def lockstep_compare(product, oracle, actions, *, resync, rtol, floor, reward_floor=10.0, obs_floor=0.1,
-                     num_obstacles=2, report=None):
+                     small_floor=None, num_obstacles=2, report=None):
     """Step `product` and `oracle` with the same actions [T,N,3] (auto-reset on, same scenes).
 
     Bit-exact: K, cycle, phase, terminated, truncated (hence the reset indices), episode index.
@@ -241,7 +241,10 @@ def lockstep_compare(product, oracle, actions, *, resync, rtol, floor, reward_fl
             ref = oracle.get_state(col)
             got = product.get_state(col)
             ok = np.isfinite(ref)
-            e = rel_err(got[ok], ref[ok], floor)
+            # out-of-plane channels are excited only by rounding-level asymmetries (nozzle direction
+            # z ~ 2e-16): they are noise-driven and compared against an absolute floor
+            fl = max(floor, small_floor or 1e-4) if col in SMALL_CHANNELS else floor
+            e = rel_err(got[ok], ref[ok], fl)
             errs[col] = float(e.max()) if e.size else 0.0
         rew_o64, rew_p64 = oracle.terms[:, 7], product.terms[:, 7]      # float64 totals (io.reward is float32)
         ok = np.isfinite(rew_o64)

