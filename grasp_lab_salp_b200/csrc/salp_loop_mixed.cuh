@@ -223,18 +223,108 @@ SALP_HD int first_k_past(const double* table, double x, double inv_dt) {
   return k;
 }
 
-// Body-to-world rotation by successive elementary rotations (dynamics.py:35-58: Rz Ry Rx v)
-#define SALP_ROTATE_TO_WORLD()                                     \
-  float u1 = cph * v1 - sph * v2, u2 = sph * v1 + cph * v2;        \
-  float r0 = cth * v0 + sth * u2, vw2 = cth * u2 - sth * v0;       \
-  vw0 = cps * r0 - sps * u1;                                       \
-  vw1 = sps * r0 + cps * u1;
+// fp32 register state of one env inside the substep loop
+struct Motion32 {
+  float v0, v1, v2, w0, w1, w2;          // velocity, angular_velocity (body frame)
+  float ac0, ac1, ac2, al0, al1, al2;    // previous substep's accelerations (robot.py:806, 992, 1005)
+  float phi, theta;                      // roll, pitch
+  float sph, cph, sth, cth;              // their sin / cos (carried: the Euler-rate matrix uses the OLD angles)
+  float sps, cps;                        // sin / cos of yaw = chunk base (fp64) rotated by the fp32 increments
+  float psi_lo;                          // yaw accumulated since the last flush
+  float pw0, pw1, pw2;                   // chunk partial sums: position_world, position, angle
+  float pos0, pos1, pos2, ang0, ang1, ang2;
+  float vw0, vw1;                        // velocity_world[0:2] of the latest kinematic update
+};
+
+// _newton_equations + _euler_equations + the velocity half of _update_motion_states
+// (robot.py:789-862) in the pre-divided form documented at Coef32.  ~80 FP32 instructions.
+SALP_HD void dyn_step(const SalpDerived& dv, const Coef32& g, Motion32& s) {
+  const float v0 = s.v0, v1 = s.v1, v2 = s.v2, w0 = s.w0, w1 = s.w1, w2 = s.w2;
+  float sd = fast_norm3(v0, v1, v2) + dv.ratio_f;               // |v| v + ratio v = v (|v| + ratio)
+  float wn = fast_norm3(w0, w1, w2);
+  float ev0 = dv.E[0] * v0, ev1 = dv.E[1] * v1, ev2 = dv.E[2] * v2;
+  float t1 = w2 * g.com, t2 = -w1 * g.com;                      // w x c, c = (com, 0, 0)   robot.py:806-810
+  float fict0 = (w1 * t2 - w2 * t1) + g.com_acc;
+  float fict1 = fmaf(s.al2, g.com, fmaf(2.0f * w2, g.com_rate, -w0 * t2));
+  float fict2 = fmaf(-s.al1, g.com, fmaf(-2.0f * w1, g.com_rate, w0 * t1));
+  float na0 = g.aj[0] + v0 * fmaf(g.kdm[0], sd, -g.mrm[0]) - dv.Ca[0] * s.ac0 - (w1 * ev2 - w2 * ev1) + fict0;
+  float na1 = g.aj[1] + v1 * fmaf(g.kdm[1], sd, -g.mrm[1]) - dv.Ca[1] * s.ac1 - (w2 * ev0 - w0 * ev2) + fict1;
+  float na2 = g.aj[2] + v2 * fmaf(g.kdm[2], sd, -g.mrm[2]) - dv.Ca[2] * s.ac2 - (w0 * ev1 - w1 * ev0) + fict2;
+  float nl0 = w0 * fmaf(g.kqI[0], wn, g.klI[0]) - dv.Cat[0] * s.al0 - (w1 * w2) * g.JdI[0] - (v1 * v2) * g.AdI[0];
+  float nl1 = g.tj1 + w1 * fmaf(g.kqI[1], wn, g.klI[1]) - dv.Cat[1] * s.al1 - (w2 * w0) * g.JdI[1] - (v2 * v0) * g.AdI[1];
+  float nl2 = g.tj2 + w2 * fmaf(g.kqI[2], wn, g.klI[2]) - dv.Cat[2] * s.al2 - (w0 * w1) * g.JdI[2] - (v0 * v1) * g.AdI[2];
+  s.ac0 = na0; s.ac1 = na1; s.ac2 = na2;
+  s.al0 = nl0; s.al1 = nl1; s.al2 = nl2;
+  s.v0 = fmaf(na0, dv.dt, v0); s.v1 = fmaf(na1, dv.dt, v1); s.v2 = fmaf(na2, dv.dt, v2);
+  s.w0 = fmaf(nl0, dv.dt, w0); s.w1 = fmaf(nl1, dv.dt, w1); s.w2 = fmaf(nl2, dv.dt, w2);
+}
+
+// The kinematic half of _update_motion_states (robot.py:864-875): Euler-angle rates at the old
+// roll/pitch (dynamics.py:21-31), new angles, body->world rotation Rz Ry Rx (dynamics.py:35-58) by
+// successive elementary rotations, the three position/angle integrals.  ~65 FP32 instructions.
+// v, w are the velocities AFTER dyn_step of the same substep.
+template <bool WIDE>
+SALP_HD void kin_step(const SalpDerived& dv, Motion32& s) {
+  const float dt = dv.dt;
+  const float v0 = s.v0, v1 = s.v1, v2 = s.v2, w0 = s.w0, w1 = s.w1, w2 = s.w2;
+  float rcth = fast_rcp(s.cth);
+  float q = s.sph * w1 + s.cph * w2;
+  float er0 = fmaf(s.sth * rcth, q, w0);
+  float er1 = s.cph * w1 - s.sph * w2;
+  float dpsi = (q * rcth) * dt;
+  s.phi = fmaf(er0, dt, s.phi);
+  s.theta = fmaf(er1, dt, s.theta);
+  s.psi_lo += dpsi;
+  if (WIDE) { sincos32(s.phi, s.sph, s.cph); sincos32(s.theta, s.sth, s.cth); }
+  else { sincos_small(s.phi, s.sph, s.cph); sincos_small(s.theta, s.sth, s.cth); }
+  float sd_, cd_;
+  sincos_small(dpsi, sd_, cd_);                                 // yaw: rotate (sin, cos) by the increment
+  float ns = s.sps * cd_ + s.cps * sd_;
+  s.cps = s.cps * cd_ - s.sps * sd_;
+  s.sps = ns;
+  float u1 = s.cph * v1 - s.sph * v2, u2 = s.sph * v1 + s.cph * v2;      // Rx
+  float r0 = s.cth * v0 + s.sth * u2, vw2 = s.cth * u2 - s.sth * v0;     // Ry
+  s.vw0 = s.cps * r0 - s.sps * u1;                                       // Rz
+  s.vw1 = s.sps * r0 + s.cps * u1;
+  s.pw0 = fmaf(s.vw0, dt, s.pw0); s.pw1 = fmaf(s.vw1, dt, s.pw1); s.pw2 = fmaf(vw2, dt, s.pw2);
+  s.pos0 = fmaf(v0, dt, s.pos0); s.pos1 = fmaf(v1, dt, s.pos1); s.pos2 = fmaf(v2, dt, s.pos2);
+  s.ang0 = fmaf(w0, dt, s.ang0); s.ang1 = fmaf(w1, dt, s.ang1); s.ang2 = fmaf(w2, dt, s.ang2);
+}
+
+// Shape bookkeeping in fp64 (everything the reference differences) + the fp32 coefficient set.
+struct ShapeTrack {
+  Shape64 s;
+  double prev_com_rate, com_acc, prevV, I0_prev_used, I1_prev_used, dl;
+  int last_update;
+};
+
+// update_state + update_properties after substep j-1 (robot.py:640-668), only called while the
+// shape moves or its backward differences have not been flushed yet.
+SALP_HD void shape_update(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c, const double* time_table,
+                          const float dir[3], int j, int k_T0, int k_jet, ShapeTrack& st, Coef32& g) {
+  const double t = time_table[j];
+  const int phase = j < k_T0 ? 0 : (j < k_jet ? 1 : 2);
+  st.dl = shape_delta(phase, t, c.refill, c.T0, (double)c.contraction32, c.contract_rate, c.release_rate);
+  double lh = 0.5 * (p.init_length - st.dl), wh = 0.5 * (p.init_width + st.dl);
+  double V, I0n, I1n, com, wm;
+  shape64_at(p, dv, lh, wh, V, I0n, I1n, com, wm);
+  double dV_dt = (V - st.s.V) * dv.inv_dt;
+  double com_rate = (com - st.s.com) * dv.inv_dt;                // robot.py:901-910
+  st.com_acc = (com_rate - st.prev_com_rate) * dv.inv_dt;        // robot.py:912-922
+  st.prev_com_rate = com_rate;
+  make_coefs(dv, dir, phase == 1, (float)lh, (float)wh, (float)(dv.m0 + wm), (float)I0n, (float)I1n,
+             (float)((I0n - st.s.I0) * dv.inv_dt), (float)((I1n - st.s.I1) * dv.inv_dt),
+             (float)(p.density * dV_dt), (float)dV_dt, (float)com, (float)com_rate, (float)st.com_acc, g);
+  st.prevV = st.s.V;
+  st.I0_prev_used = st.s.I0;
+  st.I1_prev_used = st.s.I1;
+  st.s.V = V; st.s.I0 = I0n; st.s.I1 = I1n; st.s.com = com; st.s.com_rate = com_rate;
+  st.last_update = j;
+}
 
 template <>
 SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c,
                                             const double* time_table, Body64& b, double& t_out) {
-  const float dt = dv.dt;
-
   // ---- K: first k with !(t_k < total) in the dtype the reference compares in (robot.py:756) ----
   const int K = plan_substeps(c, time_table);
   t_out = 0.0;
@@ -253,186 +343,125 @@ SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDeriv
   const float dir[3] = {(float)c.dir[0], (float)c.dir[1], (float)c.dir[2]};
 
   // ---- prologue: shape-derived state of the first substep from the carried columns ----
-  Shape64 s;
+  ShapeTrack st;
   Coef32 g;
-  double prev_com_rate = b.prev_com_rate;
-  double com_acc64 = b.com_acc;
-  double prevV = b.prev_volume;
-  double I0_prev_used, I1_prev_used;     // inertia used by the latest substep's Euler equations (robot.py:896)
-  double dl = 0.0;
+  st.prev_com_rate = b.prev_com_rate;
+  st.com_acc = b.com_acc;
+  st.prevV = b.prev_volume;
+  st.dl = 0.0;
+  st.last_update = 0;
   {
     double lh = 0.5 * b.length, wh = 0.5 * b.width, wm, com_now;
-    shape64_at(p, dv, lh, wh, s.V, s.I0, s.I1, com_now, wm);
-    double dV_dt = (s.V - b.prev_volume) * dv.inv_dt;
+    shape64_at(p, dv, lh, wh, st.s.V, st.s.I0, st.s.I1, com_now, wm);
+    double dV_dt = (st.s.V - b.prev_volume) * dv.inv_dt;
     // the carried centre of mass may be stale w.r.t. length/width (Robot.reset quirk, robot.py:478)
-    s.com = b.com;
-    s.com_rate = b.com_rate;
-    make_coefs(dv, dir, b.phase == 1, (float)lh, (float)wh, (float)(dv.m0 + wm), (float)s.I0, (float)s.I1,
-               (float)((s.I0 - b.prevI[0]) * dv.inv_dt), (float)((s.I1 - b.prevI[1]) * dv.inv_dt),
+    st.s.com = b.com;
+    st.s.com_rate = b.com_rate;
+    make_coefs(dv, dir, b.phase == 1, (float)lh, (float)wh, (float)(dv.m0 + wm), (float)st.s.I0, (float)st.s.I1,
+               (float)((st.s.I0 - b.prevI[0]) * dv.inv_dt), (float)((st.s.I1 - b.prevI[1]) * dv.inv_dt),
                (float)(p.density * dV_dt), (float)dV_dt, (float)b.com, (float)b.com_rate, (float)b.com_acc, g);
-    I0_prev_used = s.I0;
-    I1_prev_used = s.I1;
+    st.I0_prev_used = st.s.I0;
+    st.I1_prev_used = st.s.I1;
   }
-  int last_update = 0;
 
   // ---- fp32 motion state ----
-  float v0 = (float)b.v[0], v1 = (float)b.v[1], v2 = (float)b.v[2];
-  float w0 = (float)b.w[0], w1 = (float)b.w[1], w2 = (float)b.w[2];
-  float ac0 = (float)b.acc[0], ac1 = (float)b.acc[1], ac2 = (float)b.acc[2];
-  float al0 = (float)b.alp[0], al1 = (float)b.alp[1], al2 = (float)b.alp[2];
-  float phi = (float)b.eul[0], theta = (float)b.eul[1];
-  float sph, cph, sth, cth;
-  sincos32(phi, sph, cph);
-  sincos32(theta, sth, cth);
+  Motion32 s;
+  s.v0 = (float)b.v[0]; s.v1 = (float)b.v[1]; s.v2 = (float)b.v[2];
+  s.w0 = (float)b.w[0]; s.w1 = (float)b.w[1]; s.w2 = (float)b.w[2];
+  s.ac0 = (float)b.acc[0]; s.ac1 = (float)b.acc[1]; s.ac2 = (float)b.acc[2];
+  s.al0 = (float)b.alp[0]; s.al1 = (float)b.alp[1]; s.al2 = (float)b.alp[2];
+  s.phi = (float)b.eul[0]; s.theta = (float)b.eul[1];
+  sincos32(s.phi, s.sph, s.cph);
+  sincos32(s.theta, s.sth, s.cth);
   double psi64 = b.eul[2];
-  float sps, cps;
   {
     double sb64, cb64;
     sincos(psi64, &sb64, &cb64);
-    sps = (float)sb64;
-    cps = (float)cb64;
+    s.sps = (float)sb64;
+    s.cps = (float)cb64;
   }
-  float psi_lo = 0.f, pw_lo0 = 0.f, pw_lo1 = 0.f, pw_lo2 = 0.f;
-  float pos_lo0 = 0.f, pos_lo1 = 0.f, pos_lo2 = 0.f, ang_lo0 = 0.f, ang_lo1 = 0.f, ang_lo2 = 0.f;
-  float vw0 = 0.f, vw1 = 0.f;
-  // The kinematic update (Euler angles, world position, body-frame integrals; robot.py:864-875)
-  // of substep k-1 only READS the (v, w) that the dynamics of substep k also only reads, so it
-  // is issued one iteration late, side by side with the next substep's force/torque chains: two
-  // independent dependency chains per iteration instead of one long one.  kdt = 0 turns the
-  // (not yet due) kinematic update of iteration 0 into a no-op.
-  float kdt = 0.0f;
+  s.psi_lo = 0.f; s.pw0 = s.pw1 = s.pw2 = 0.f;
+  s.pos0 = s.pos1 = s.pos2 = 0.f; s.ang0 = s.ang1 = s.ang2 = 0.f;
+  s.vw0 = s.vw1 = 0.f;
 
-  for (int k0 = 0; k0 < K; k0 += SALP_MIXED_CHUNK) {
-    const int kend = k0 + SALP_MIXED_CHUNK < K ? k0 + SALP_MIXED_CHUNK : K;
+  // The kinematic update of substep k-1 only READS the (v, w) that the dynamics of substep k also
+  // only reads, so the loop runs kin(k-1) side by side with dyn(k): two independent dependency
+  // chains per iteration instead of one long one.  Substep 0's dynamics is peeled off in front,
+  // substep K-1's kinematics behind.
+  int next_upd;                     // next update index j at which the shape (or its differences) moves
+  dyn_step(dv, g, s);
+  shape_update(p, dv, c, time_table, dir, 1, k_T0, k_jet, st, g);
+  next_upd = 2;
+
+#define SALP_AFTER_SUBSTEP(j)                                                                   \
+  if ((j) == next_upd) {                                                                        \
+    shape_update(p, dv, c, time_table, dir, (j), k_T0, k_jet, st, g);                           \
+    next_upd = ((j) < upd_a_end || ((j) >= upd_b_begin && (j) < upd_b_end)) ? (j) + 1           \
+               : ((j) < upd_b_begin ? upd_b_begin : 0x7fffffff);                                \
+  }
+
+  int k = 1;
+  while (k < K) {
+    const int kend = k + SALP_MIXED_CHUNK < K ? k + SALP_MIXED_CHUNK : K;
     // roll / pitch move by < 0.1 rad per chunk; beyond 0.45 rad the chunk takes the range-reduced path
-    const bool wide = fabsf(phi) > 0.45f || fabsf(theta) > 0.45f;
-    for (int k = k0; k < kend; k++) {
-      // ---- kinematics of the previous substep (robot.py:864-875) ----
-      {
-        float rcth = fast_rcp(cth);                              // dynamics.py:21-31 at the OLD roll/pitch
-        float q = sph * w1 + cph * w2;
-        float er0 = fmaf(sth * rcth, q, w0);
-        float er1 = cph * w1 - sph * w2;
-        float dpsi = (q * rcth) * kdt;
-        phi = fmaf(er0, kdt, phi);
-        theta = fmaf(er1, kdt, theta);
-        psi_lo += dpsi;
-        if (wide) { sincos32(phi, sph, cph); sincos32(theta, sth, cth); }
-        else { sincos_small(phi, sph, cph); sincos_small(theta, sth, cth); }
-        float sd_, cd_;
-        sincos_small(dpsi, sd_, cd_);                            // yaw: rotate (sin, cos) by the increment
-        float ns = sps * cd_ + cps * sd_;
-        cps = cps * cd_ - sps * sd_;
-        sps = ns;
-        SALP_ROTATE_TO_WORLD();
-        pw_lo0 = fmaf(vw0, kdt, pw_lo0); pw_lo1 = fmaf(vw1, kdt, pw_lo1); pw_lo2 = fmaf(vw2, kdt, pw_lo2);
-        pos_lo0 = fmaf(v0, kdt, pos_lo0); pos_lo1 = fmaf(v1, kdt, pos_lo1); pos_lo2 = fmaf(v2, kdt, pos_lo2);
-        ang_lo0 = fmaf(w0, kdt, ang_lo0); ang_lo1 = fmaf(w1, kdt, ang_lo1); ang_lo2 = fmaf(w2, kdt, ang_lo2);
-        kdt = dt;
+    if (fabsf(s.phi) < 0.45f && fabsf(s.theta) < 0.45f) {
+      for (; k < kend; k++) {
+        kin_step<false>(dv, s);
+        dyn_step(dv, g, s);
+        SALP_AFTER_SUBSTEP(k + 1)
       }
-      // ---- _newton_equations (robot.py:789-823) ----
-      float sd = fast_norm3(v0, v1, v2) + dv.ratio_f;            // |v| v + ratio v = v (|v| + ratio)
-      float ev0 = dv.E[0] * v0, ev1 = dv.E[1] * v1, ev2 = dv.E[2] * v2;
-      float t1 = w2 * g.com, t2 = -w1 * g.com;                   // w x c, c = (com, 0, 0)   robot.py:806-810
-      float fict0 = (w1 * t2 - w2 * t1) + g.com_acc;
-      float fict1 = fmaf(al2, g.com, fmaf(2.0f * w2, g.com_rate, -w0 * t2));
-      float fict2 = fmaf(-al1, g.com, fmaf(-2.0f * w1, g.com_rate, w0 * t1));
-      float na0 = g.aj[0] + v0 * fmaf(g.kdm[0], sd, -g.mrm[0]) - dv.Ca[0] * ac0 - (w1 * ev2 - w2 * ev1) + fict0;
-      float na1 = g.aj[1] + v1 * fmaf(g.kdm[1], sd, -g.mrm[1]) - dv.Ca[1] * ac1 - (w2 * ev0 - w0 * ev2) + fict1;
-      float na2 = g.aj[2] + v2 * fmaf(g.kdm[2], sd, -g.mrm[2]) - dv.Ca[2] * ac2 - (w0 * ev1 - w1 * ev0) + fict2;
-      // ---- _euler_equations (robot.py:825-851) ----
-      float wn = fast_norm3(w0, w1, w2);
-      float nl0 = w0 * fmaf(g.kqI[0], wn, g.klI[0]) - dv.Cat[0] * al0 - (w1 * w2) * g.JdI[0] - (v1 * v2) * g.AdI[0];
-      float nl1 = g.tj1 + w1 * fmaf(g.kqI[1], wn, g.klI[1]) - dv.Cat[1] * al1 - (w2 * w0) * g.JdI[1] - (v2 * v0) * g.AdI[1];
-      float nl2 = g.tj2 + w2 * fmaf(g.kqI[2], wn, g.klI[2]) - dv.Cat[2] * al2 - (w0 * w1) * g.JdI[2] - (v0 * v1) * g.AdI[2];
-      ac0 = na0; ac1 = na1; ac2 = na2;
-      al0 = nl0; al1 = nl1; al2 = nl2;
-      // ---- _update_motion_states, velocities (robot.py:861-862) ----
-      v0 = fmaf(ac0, dt, v0); v1 = fmaf(ac1, dt, v1); v2 = fmaf(ac2, dt, v2);
-      w0 = fmaf(al0, dt, w0); w1 = fmaf(al1, dt, w1); w2 = fmaf(al2, dt, w2);
-
-      // ---- cycle_time += dt; update_state; update_properties (robot.py:674-678, 640-668) ----
-      const int j = k + 1;
-      if (j <= upd_a_end || (j >= upd_b_begin && j <= upd_b_end)) {
-        const double t = time_table[j];
-        const int phase = j < k_T0 ? 0 : (j < k_jet ? 1 : 2);
-        dl = shape_delta(phase, t, c.refill, c.T0, (double)c.contraction32, c.contract_rate, c.release_rate);
-        double lh = 0.5 * (p.init_length - dl), wh = 0.5 * (p.init_width + dl);
-        double V, I0n, I1n, com, wm;
-        shape64_at(p, dv, lh, wh, V, I0n, I1n, com, wm);
-        double dV_dt = (V - s.V) * dv.inv_dt;
-        double com_rate = (com - s.com) * dv.inv_dt;                // robot.py:901-910
-        com_acc64 = (com_rate - prev_com_rate) * dv.inv_dt;         // robot.py:912-922
-        prev_com_rate = com_rate;
-        make_coefs(dv, dir, phase == 1, (float)lh, (float)wh, (float)(dv.m0 + wm), (float)I0n, (float)I1n,
-                   (float)((I0n - s.I0) * dv.inv_dt), (float)((I1n - s.I1) * dv.inv_dt),
-                   (float)(p.density * dV_dt), (float)dV_dt, (float)com, (float)com_rate, (float)com_acc64, g);
-        prevV = s.V;
-        I0_prev_used = s.I0;
-        I1_prev_used = s.I1;
-        s.V = V; s.I0 = I0n; s.I1 = I1n; s.com = com; s.com_rate = com_rate;
-        last_update = j;
+    } else {
+      for (; k < kend; k++) {
+        kin_step<true>(dv, s);
+        dyn_step(dv, g, s);
+        SALP_AFTER_SUBSTEP(k + 1)
       }
     }
     // two-level sums: fold the fp32 chunk partials into the fp64 totals, re-anchor sin/cos(yaw)
-    b.pw[0] += (double)pw_lo0; b.pw[1] += (double)pw_lo1; b.pw[2] += (double)pw_lo2;
-    b.pos[0] += (double)pos_lo0; b.pos[1] += (double)pos_lo1; b.pos[2] += (double)pos_lo2;
-    b.ang[0] += (double)ang_lo0; b.ang[1] += (double)ang_lo1; b.ang[2] += (double)ang_lo2;
-    psi64 += (double)psi_lo;
+    b.pw[0] += (double)s.pw0; b.pw[1] += (double)s.pw1; b.pw[2] += (double)s.pw2;
+    b.pos[0] += (double)s.pos0; b.pos[1] += (double)s.pos1; b.pos[2] += (double)s.pos2;
+    b.ang[0] += (double)s.ang0; b.ang[1] += (double)s.ang1; b.ang[2] += (double)s.ang2;
+    psi64 += (double)s.psi_lo;
     {
       double sb64, cb64;
       sincos(psi64, &sb64, &cb64);
-      sps = (float)sb64;
-      cps = (float)cb64;
+      s.sps = (float)sb64;
+      s.cps = (float)cb64;
     }
-    psi_lo = 0.f; pw_lo0 = pw_lo1 = pw_lo2 = 0.f;
-    pos_lo0 = pos_lo1 = pos_lo2 = 0.f; ang_lo0 = ang_lo1 = ang_lo2 = 0.f;
+    s.psi_lo = 0.f; s.pw0 = s.pw1 = s.pw2 = 0.f;
+    s.pos0 = s.pos1 = s.pos2 = 0.f; s.ang0 = s.ang1 = s.ang2 = 0.f;
   }
-  // ---- the last substep's kinematic update (pipelined one iteration late) ----
-  {
-    float rcth = fast_rcp(cth);
-    float q = sph * w1 + cph * w2;
-    float er0 = fmaf(sth * rcth, q, w0);
-    float er1 = cph * w1 - sph * w2;
-    float dpsi = (q * rcth) * dt;
-    phi = fmaf(er0, dt, phi);
-    theta = fmaf(er1, dt, theta);
-    sincos32(phi, sph, cph);
-    sincos32(theta, sth, cth);
-    psi64 += (double)dpsi;
-    double sb64, cb64;
-    sincos(psi64, &sb64, &cb64);
-    sps = (float)sb64;
-    cps = (float)cb64;
-    SALP_ROTATE_TO_WORLD();
-    b.pw[0] += (double)(vw0 * dt); b.pw[1] += (double)(vw1 * dt); b.pw[2] += (double)(vw2 * dt);
-    b.pos[0] += (double)(v0 * dt); b.pos[1] += (double)(v1 * dt); b.pos[2] += (double)(v2 * dt);
-    b.ang[0] += (double)(w0 * dt); b.ang[1] += (double)(w1 * dt); b.ang[2] += (double)(w2 * dt);
-  }
+#undef SALP_AFTER_SUBSTEP
+  // ---- the last substep's kinematic update ----
+  kin_step<true>(dv, s);
+  b.pw[0] += (double)s.pw0; b.pw[1] += (double)s.pw1; b.pw[2] += (double)s.pw2;
+  b.pos[0] += (double)s.pos0; b.pos[1] += (double)s.pos1; b.pos[2] += (double)s.pos2;
+  b.ang[0] += (double)s.ang0; b.ang[1] += (double)s.ang1; b.ang[2] += (double)s.ang2;
+  psi64 += (double)s.psi_lo;
 
   // ---- epilogue: back to the carried fp64 columns ----
-  if (last_update != K) {        // static tail: update_properties re-assigned the same shape (robot.py:651-668)
-    prevV = s.V;
-    I0_prev_used = s.I0;
-    I1_prev_used = s.I1;
+  if (st.last_update != K) {     // static tail: update_properties re-assigned the same shape (robot.py:651-668)
+    st.prevV = st.s.V;
+    st.I0_prev_used = st.s.I0;
+    st.I1_prev_used = st.s.I1;
   }
   const double tK = time_table[K];
-  b.v[0] = v0; b.v[1] = v1; b.v[2] = v2;
-  b.w[0] = w0; b.w[1] = w1; b.w[2] = w2;
-  b.acc[0] = ac0; b.acc[1] = ac1; b.acc[2] = ac2;
-  b.alp[0] = al0; b.alp[1] = al1; b.alp[2] = al2;
-  b.eul[0] = phi; b.eul[1] = theta; b.eul[2] = psi64;
+  b.v[0] = s.v0; b.v[1] = s.v1; b.v[2] = s.v2;
+  b.w[0] = s.w0; b.w[1] = s.w1; b.w[2] = s.w2;
+  b.acc[0] = s.ac0; b.acc[1] = s.ac1; b.acc[2] = s.ac2;
+  b.alp[0] = s.al0; b.alp[1] = s.al1; b.alp[2] = s.al2;
+  b.eul[0] = s.phi; b.eul[1] = s.theta; b.eul[2] = psi64;
   b.phase = phase_at(c, tK);
-  b.length = p.init_length - dl;
-  b.width = p.init_width + dl;
-  b.prev_volume = prevV;
-  b.prevI[0] = I0_prev_used; b.prevI[1] = I1_prev_used; b.prevI[2] = I1_prev_used;
-  b.com = s.com;
-  b.prev_com = s.com;
-  b.com_rate = s.com_rate;
-  b.prev_com_rate = prev_com_rate;
-  b.com_acc = com_acc64;
-  b.speed_world = (double)sqrtf(vw0 * vw0 + vw1 * vw1);
+  b.length = p.init_length - st.dl;
+  b.width = p.init_width + st.dl;
+  b.prev_volume = st.prevV;
+  b.prevI[0] = st.I0_prev_used; b.prevI[1] = st.I1_prev_used; b.prevI[2] = st.I1_prev_used;
+  b.com = st.s.com;
+  b.prev_com = st.s.com;
+  b.com_rate = st.s.com_rate;
+  b.prev_com_rate = st.prev_com_rate;
+  b.com_acc = st.com_acc;
+  b.speed_world = (double)sqrtf(s.vw0 * s.vw0 + s.vw1 * s.vw1);
   t_out = tK;
   return K;
 }
