@@ -263,6 +263,17 @@ SALP_HD void env_step(const SalpParams& p, const SalpDerived& dv, const SalpView
   if (K < 0) raise_status(v, SALP_ERR_RANGE);
   store_body(c, b);
 
+  // Where the reference RAISES: a cycle whose contraction makes jet_time a fraction of one substep
+  // (a0 in about [0.0905, 0.094]) drives the semi-implicit Euler integrator unstable, the state
+  // overflows, and np.linalg.solve inside dynamics.py:6-10 throws LinAlgError("Array must not
+  // contain infs or NaNs") -- the reference process dies.  A batch cannot raise per env: the env
+  // is truncated instead (reward = -out_of_bounds_penalty, observation sanitised to finite
+  // values, episode metric SALP_EM_NONFINITE = 1) as soon as its state is non-finite at the end
+  // of a cycle, which is at most one env-step earlier than the reference's exception.
+  const bool crashed = !(isfinite(b.v[0]) && isfinite(b.v[1]) && isfinite(b.v[2]) && isfinite(b.w[0]) &&
+                         isfinite(b.w[1]) && isfinite(b.w[2]) && isfinite(b.pw[0]) && isfinite(b.pw[1]) &&
+                         isfinite(b.pw[2]) && isfinite(b.eul[0]) && isfinite(b.eul[1]) && isfinite(b.eul[2]));
+
   // :238-243
   const double path = c.d(SALP_F_EP_PATH_LENGTH) + norm2d(b.pw[0] - last_x, b.pw[1] - last_y);
   c.d(SALP_F_EP_PATH_LENGTH) = path;
@@ -319,6 +330,13 @@ SALP_HD void env_step(const SalpParams& p, const SalpDerived& dv, const SalpView
   else if (dist > p.out_of_bounds_distance) { trunc = true; rew -= p.out_of_bounds_penalty; }
   if (hit) { trunc = true; rew -= p.collision_penalty; }
   if (cycle >= p.max_cycles) { trunc = true; rew -= p.timeout_penalty; }
+  if (crashed) {
+    done = false;
+    trunc = true;
+    for (int k = 0; k < 7; k++) terms[k] = 0.0;
+    rew = -p.out_of_bounds_penalty;
+    for (int k = 0; k < D; k++) obs[k] = isfinite(obs[k]) ? obs[k] : 0.0f;
+  }
 
   // episode bookkeeping (:199, :247-248, Monitor)
   c.n(SALP_F_EP_LENGTH) = ep_len + 1;
@@ -333,8 +351,14 @@ SALP_HD void env_step(const SalpParams& p, const SalpDerived& dv, const SalpView
   c.f(SALP_F_PREV_ACTION2) = a2;
 
   const bool ended = done || trunc;
-  if (io.episode_metrics && ended)
-    write_episode_metrics(c, b.pw[0], b.pw[1], dist, ep_len + 1, io.episode_metrics + i * SALP_NUM_EPISODE_METRICS);
+  if (io.episode_metrics && ended) {
+    double* m = io.episode_metrics + i * SALP_NUM_EPISODE_METRICS;
+    write_episode_metrics(c, b.pw[0], b.pw[1], dist, ep_len + 1, m);
+    if (crashed) {
+      for (int k = 0; k < SALP_NUM_EPISODE_METRICS; k++) m[k] = isfinite(m[k]) ? m[k] : 0.0;
+      m[SALP_EM_NONFINITE] = 1.0;
+    }
+  }
   io.reward[i] = (float)rew;
   io.terminated[i] = done ? 1 : 0;
   io.truncated[i] = trunc ? 1 : 0;

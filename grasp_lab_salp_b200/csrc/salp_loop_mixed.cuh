@@ -404,7 +404,7 @@ SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDeriv
   while (k < K) {
     const int kend = k + SALP_MIXED_CHUNK < K ? k + SALP_MIXED_CHUNK : K;
     // roll / pitch move by < 0.1 rad per chunk; beyond 0.45 rad the chunk takes the range-reduced path
-    if (fabsf(s.phi) < 0.45f && fabsf(s.theta) < 0.45f) {
+    if (!(fabsf(s.phi) >= 0.45f || fabsf(s.theta) >= 0.45f)) {     // (NaN counts as narrow: the env is being cut anyway)
       for (; k < kend; k++) {
         kin_step<false>(dv, s);
         dyn_step(dv, g, s);

@@ -31,7 +31,7 @@ EPISODE_METRIC_NAMES = (
     "initial_distance", "avg_compression", "avg_coast_time", "avg_nozzle_angle", "avg_velocity",
     "avg_rewards_track", "avg_rewards_heading", "avg_rewards_smooth", "avg_rewards_yaw",
     "avg_rewards_time", "avg_rewards_sideslip", "avg_rewards_obstacle", "total_substeps",
-    "reserved")
+    "nonfinite")
 
 
 class SalpParams(C.Structure):

@@ -122,7 +122,7 @@ typedef enum SalpEpisodeMetric {
   SALP_EM_AVG_VELOCITY = 10,
   SALP_EM_AVG_REWARD_TRACK = 11,  /* ..17: avg_rewards_{track,heading,smooth,yaw,time,sideslip,obstacle} */
   SALP_EM_TOTAL_SUBSTEPS = 18,
-  SALP_EM_RESERVED = 19
+  SALP_EM_NONFINITE = 19        /* 1.0 if the episode was cut because the state became non-finite (see salp_step) */
 } SalpEpisodeMetric;
 
 /*
@@ -205,7 +205,14 @@ int salp_reset(salp_handle h, const uint8_t* mask_dev, float* obs_dev, void* str
  * solve_angles (robot.py:62-98), Robot.set_control (:544-592), Robot.step_through_cycle
  * (:740-776) and the K x Robot.step() substep loop (:670-678) with every dynamics.py /
  * geometry.py function under it; plus, with SALP_STEP_AUTORESET, the auto-reset that SB3's
- * DummyVecEnv/SubprocVecEnv worker performs around it. */
+ * DummyVecEnv/SubprocVecEnv worker performs around it.
+ *
+ * Where the reference raises: some contractions (a0 in about [0.0905, 0.094], jet_time a
+ * fraction of one substep) make the reference's integrator diverge; its state overflows and
+ * np.linalg.solve (dynamics.py:6-10) throws LinAlgError, i.e. the reference process dies.  A
+ * batched call cannot raise per env: such an env is TRUNCATED in the step whose cycle left its
+ * state non-finite (truncated = 1, terminated = 0, reward = -out_of_bounds_penalty, observation
+ * with non-finite entries replaced by 0, episode metric SALP_EM_NONFINITE = 1). */
 int salp_step(salp_handle h, const SalpStepIO* io_dev, uint32_t flags, void* stream);
 
 /* Same two calls with HOST buffers: H2D of actions, the kernels, D2H of every non-null

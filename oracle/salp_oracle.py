@@ -44,6 +44,8 @@ def lib():
         L.orc_step.argtypes = [C.c_void_p] + [C.c_void_p] * 9 + [C.c_int, C.c_int64, C.c_int64]
         L.orc_get_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_get_state.restype = C.c_int
+        L.orc_set_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_set_state.restype = C.c_int
         L.orc_get_cycle_plan.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_np_sincosf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         _lib = L
@@ -140,6 +142,11 @@ class OracleVecEnv:
         if rc != 0:
             raise KeyError(name)
         return out
+
+    def set_state(self, name: str, values):
+        v = np.ascontiguousarray(np.broadcast_to(values, (self.num_envs,)), field_dtype(name))
+        if lib().orc_set_state(self._h, field_id(name), _ptr(v)) != 0:
+            raise KeyError(name)
 
     def cycle_plan(self) -> np.ndarray:
         """[N,5]: refill_time, jet_time, turn_time, total, total_is_float32 of the last step."""

@@ -279,3 +279,30 @@ def sample_scene_pool(rng, n_envs, P, num_obstacles=2, lo=(-2.0, -1.5), hi=(2.0,
             targets[i, s] = t
             obstacles[i, s] = np.array(obs).reshape(num_obstacles, 2)
     return targets, obstacles
+
+
+def check_blowup_golden(make_backend):
+    """tests/golden/ref_blowup.npz: 512 single cycles from rest (carried nozzle angles injected)
+    with contractions around the zero crossings of the reference's refill/jet-time polynomials;
+    in 16 of them the live reference raised LinAlgError (its state overflowed).  The backend
+    must cut exactly those episodes (truncated, reward -200, metric `nonfinite` = 1, finite
+    observation) and reproduce K and the final pose of all the others."""
+    g = load_golden("ref_blowup.npz")
+    n = len(g["actions"])
+    env = make_backend(n, g)
+    env.set_scene_pool(np.tile(np.array([[[1.8, 1.2]]], np.float32), (n, 1, 1)),
+                       np.tile(np.array([[[[-1.5, -1.0], [1.5, -1.0]]]], np.float32), (n, 1, 1, 1)))
+    env.reset()
+    env.set_state("nozzle_angle1", g["angle1"])
+    env.set_state("nozzle_angle2", g["angle2"])
+    obs, rew, term, trunc = env.step(g["actions"])
+    raised = g["raised"].astype(bool)
+    cut = (env.metrics[:, 19] == 1.0) & trunc.astype(bool)
+    np.testing.assert_array_equal(cut, raised)
+    assert np.isfinite(obs).all() and np.isfinite(rew).all()
+    np.testing.assert_array_equal(term[raised], 0)
+    np.testing.assert_allclose(rew[raised], -200.0)
+    ok = ~raised
+    np.testing.assert_array_equal(env.substeps[ok], g["substeps_run"][ok])
+    got = np.stack([env.get_state("posw_x"), env.get_state("posw_y"), env.get_state("euler_z")], axis=1)
+    return float(rel_err(got[ok], g["final"][ok], 0.1).max())

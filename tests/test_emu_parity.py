@@ -6,7 +6,7 @@ import pytest
 from emu_backend import EmuBatch
 from grasp_lab_salp_b200 import PRECISION_F64, PRECISION_MIXED
 from oracle.salp_oracle import OracleVecEnv
-from parity import TOL_F64, TOL_MIXED, TOL_MIXED_FREE_RUN, golden_params, lockstep_compare, sample_scene_pool, load_golden, replay_golden
+from parity import check_blowup_golden, TOL_F64, TOL_MIXED, TOL_MIXED_FREE_RUN, golden_params, lockstep_compare, sample_scene_pool, load_golden, replay_golden
 
 GOLDENS = ["ref_fixed10.npz", "ref_edge.npz", "ref_random.npz", "ref_clipped.npz"]
 
@@ -68,3 +68,9 @@ def test_emu_f64_lockstep_vs_oracle_with_autoreset():
     worst = max(max(h.values()) for h in hist)
     assert worst < 1e-7, worst
     assert orc.get_state("episode_index").max() > 1     # some episodes did end and auto-reset
+
+
+@pytest.mark.parametrize("precision", [PRECISION_F64, PRECISION_MIXED])
+def test_emu_cuts_exactly_the_episodes_where_the_reference_raises(precision):
+    worst = check_blowup_golden(lambda n, g: EmuBatch(n, golden_params(g, precision=precision)))
+    assert worst < (1e-9 if precision == PRECISION_F64 else 1e-5), worst

@@ -6,7 +6,7 @@ import pytest
 
 from grasp_lab_salp_b200 import PRECISION_F64, PRECISION_MIXED, SalpBatch
 from oracle.salp_oracle import OracleVecEnv
-from parity import (TOL_F64, TOL_MIXED, TOL_MIXED_FREE_RUN, golden_params, load_golden, lockstep_compare,
+from parity import (check_blowup_golden, TOL_F64, TOL_MIXED, TOL_MIXED_FREE_RUN, golden_params, load_golden, lockstep_compare,
                     replay_golden, sample_scene_pool)
 
 pytestmark = pytest.mark.gpu
@@ -204,3 +204,9 @@ def test_non_finite_action_raises_range_error_not_a_hang():
     env.step(a)
     with pytest.raises(SalpError):
         env.check()
+
+
+@pytest.mark.parametrize("precision", [PRECISION_F64, PRECISION_MIXED])
+def test_kernel_cuts_exactly_the_episodes_where_the_reference_raises(precision):
+    worst = check_blowup_golden(lambda n, g: SalpBatch(n, golden_params(g, precision=precision)))
+    assert worst < (1e-9 if precision == PRECISION_F64 else 1e-5), worst

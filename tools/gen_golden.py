@@ -119,6 +119,31 @@ def run_env(args):
     return out
 
 
+def run_blowup_case(args):
+    """One cycle from rest with given carried nozzle angles; does the reference raise?"""
+    action, angle1, angle2 = args
+    env = rh.make_env()
+    env.reset()
+    rh.inject_scene(env, [1.8, 1.2], [[-1.5, -1.0], [1.5, -1.0]])
+    env.robot.nozzle.angle1 = float(angle1)
+    env.robot.nozzle.angle2 = float(angle2)
+    counter = {"k": 0}
+    orig_step = env.robot.step
+
+    def counting_step():
+        counter["k"] += 1
+        orig_step()
+
+    env.robot.step = counting_step
+    raised = 0
+    try:
+        env.step(np.asarray(action, np.float32).copy())
+    except np.linalg.LinAlgError:
+        raised = 1
+    r = env.robot
+    return raised, counter["k"], np.array([*r.position_world[:2], r.euler_angle[2]], np.float64)
+
+
 def gather(results):
     keys = results[0].keys()
     return {k: np.stack([r[k] for r in results]) for k in keys}
@@ -143,7 +168,7 @@ def write(name, actions, targets, obstacles, note):
 
 def main():
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
-    which = sys.argv[1:] or ["fixed10", "edge", "random", "clipped"]
+    which = sys.argv[1:] or ["fixed10", "edge", "random", "clipped", "blowup"]
     rng = np.random.default_rng(20261018)
 
     if "fixed10" in which:
@@ -182,6 +207,26 @@ def main():
         a = np.clip(rng.normal(size=(n, T, 3)), [0, 0, -1], [1, 1, 1]).astype(np.float32)
         t, o = sample_scenes(rng, n, 8)
         write("ref_clipped.npz", a, t, o, "N(0,1) actions clipped to the Box (SURVEY 8d input B)")
+
+
+    if "blowup" in which:
+        # contractions whose jet_time is a fraction of one substep: the reference's integrator can
+        # diverge and np.linalg.solve then raises LinAlgError (dynamics.py:6-10)
+        n = 512
+        a = rng.uniform([0.0885, 0.0, -1.0], [0.0945, 1.0, 1.0], size=(n, 3)).astype(np.float32)
+        ang1 = rng.uniform(-np.pi, np.pi, n)
+        ang2 = rng.uniform(0.0, np.pi, n)
+        with Pool(8) as pool:
+            res = pool.map(run_blowup_case, [(a[i], ang1[i], ang2[i]) for i in range(n)])
+        m = rh.load()
+        np.savez_compressed(
+            os.path.join(ROOT, "tests", "golden", "ref_blowup.npz"), actions=a, angle1=ang1, angle2=ang2,
+            raised=np.array([r[0] for r in res], np.uint8), substeps_run=np.array([r[1] for r in res], np.int32),
+            final=np.stack([r[2] for r in res]),
+            refill_poly=m.geometry.fit_compression_refill_time_relation_jit(),
+            jet_poly=m.geometry.fit_compression_propulsion_time_relation_jit(),
+            note=np.array("one cycle from rest, carried nozzle angles injected; raised = reference threw LinAlgError"))
+        print(f"ref_blowup.npz: {n} cases, reference raised in {sum(r[0] for r in res)}")
 
 
 if __name__ == "__main__":
