@@ -111,6 +111,8 @@ int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& i
   const int block = block_for(v.n);
   if (p.precision == SALP_PRECISION_F64)
     salp_launch_step_f64(p, v, io, flags, order, stream);     // salp_step_f64.cu (compiled with -fmad=false)
+  else if (block == 32)
+    salp_step_kernel_lat<SALP_PRECISION_MIXED><<<grid_for(v.n, 32), 32, 0, stream>>>(p, make_derived(p), v, io, flags, order);
   else
     salp_step_kernel<SALP_PRECISION_MIXED><<<grid_for(v.n, block), block, 0, stream>>>(p, make_derived(p), v, io, flags, order);
   SALP_LAUNCH_CHECK();

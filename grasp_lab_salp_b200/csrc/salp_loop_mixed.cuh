@@ -14,8 +14,11 @@
 //    difference is exactly 0 in the reference too, and the ~30 geometry-derived coefficients
 //    stay in registers (phase-specialised loop, SURVEY.md hard part 3).
 //  * Integrals that grow over an episode (world position, body-frame position/angle integrals,
-//    yaw) are two-level sums: an fp32 partial per 16-substep chunk, flushed into an fp64 total.
-//    sin/cos(yaw) = angle addition of the fp64-evaluated chunk base and the fp32 chunk partial.
+//    the three Euler angles) are two-level sums: an fp32 partial per 16-substep chunk, flushed
+//    into an fp64 total.  sin/cos of each Euler angle is carried as a pair that is rotated by the
+//    small per-substep increment (10-instruction Taylor kernels, no range reduction) and
+//    re-anchored from the fp64 total at every flush, so it is valid for any angle.
+//  * kin(k-1) and dyn(k) are software-pipelined into one basic block (two independent chains).
 //  * The substep count K and the phase of every substep are decided exactly as the reference
 //    does (float32/float64 comparison quirks of SURVEY.md hard part 2) from the table t_k of
 //    k-fold repeated `cycle_time += 0.01` additions.
@@ -48,7 +51,7 @@ SALP_HD float fast_norm3(float a, float b, float c) {
 }
 
 // np_sincosf without the separately-rounded steps: same Cody-Waite + minimax kernels (1 ulp),
-// free to contract.  |x| <= 71476.  Used outside the substep loop and on the wide-angle path.
+// free to contract.  |x| <= 71476.  Used outside the substep loop (chunk anchors).
 SALP_HD void sincos32(float x, float& sn, float& cs) {
   float q = (x * 0x1.45f306p-1f + 0x1.8p+23f) - 0x1.8p+23f;
   float r = fmaf(q, -0x1.921fb0p+0f, x);
@@ -227,10 +230,11 @@ SALP_HD int first_k_past(const double* table, double x, double inv_dt) {
 struct Motion32 {
   float v0, v1, v2, w0, w1, w2;          // velocity, angular_velocity (body frame)
   float ac0, ac1, ac2, al0, al1, al2;    // previous substep's accelerations (robot.py:806, 992, 1005)
-  float phi, theta;                      // roll, pitch
-  float sph, cph, sth, cth;              // their sin / cos (carried: the Euler-rate matrix uses the OLD angles)
-  float sps, cps;                        // sin / cos of yaw = chunk base (fp64) rotated by the fp32 increments
-  float psi_lo;                          // yaw accumulated since the last flush
+  // Euler angles: fp64 totals live in Body64.eul; here the increments since the last flush and the
+  // (sin, cos) pairs, each = fp64-anchored value rotated by the fp32 increments of this chunk
+  // (sin/cos of roll and pitch are carried: the Euler-rate matrix uses the OLD angles)
+  float phi_lo, theta_lo, psi_lo;
+  float sph, cph, sth, cth, sps, cps;
   float pw0, pw1, pw2;                   // chunk partial sums: position_world, position, angle
   float pos0, pos1, pos2, ang0, ang1, ang2;
   float vw0, vw1;                        // velocity_world[0:2] of the latest kinematic update
@@ -263,25 +267,27 @@ SALP_HD void dyn_step(const SalpDerived& dv, const Coef32& g, Motion32& s) {
 // roll/pitch (dynamics.py:21-31), new angles, body->world rotation Rz Ry Rx (dynamics.py:35-58) by
 // successive elementary rotations, the three position/angle integrals.  ~65 FP32 instructions.
 // v, w are the velocities AFTER dyn_step of the same substep.
-template <bool WIDE>
+SALP_HD void rotate_small(float d, float& sn, float& cs) {     // (sin, cos)(x) -> (sin, cos)(x + d), |d| <= 0.55
+  float sd_, cd_;
+  sincos_small(d, sd_, cd_);
+  float ns = sn * cd_ + cs * sd_;
+  cs = cs * cd_ - sn * sd_;
+  sn = ns;
+}
 SALP_HD void kin_step(const SalpDerived& dv, Motion32& s) {
   const float dt = dv.dt;
   const float v0 = s.v0, v1 = s.v1, v2 = s.v2, w0 = s.w0, w1 = s.w1, w2 = s.w2;
   float rcth = fast_rcp(s.cth);
   float q = s.sph * w1 + s.cph * w2;
-  float er0 = fmaf(s.sth * rcth, q, w0);
-  float er1 = s.cph * w1 - s.sph * w2;
+  float dphi = fmaf(s.sth * rcth, q, w0) * dt;
+  float dtheta = (s.cph * w1 - s.sph * w2) * dt;
   float dpsi = (q * rcth) * dt;
-  s.phi = fmaf(er0, dt, s.phi);
-  s.theta = fmaf(er1, dt, s.theta);
+  s.phi_lo += dphi;
+  s.theta_lo += dtheta;
   s.psi_lo += dpsi;
-  if (WIDE) { sincos32(s.phi, s.sph, s.cph); sincos32(s.theta, s.sth, s.cth); }
-  else { sincos_small(s.phi, s.sph, s.cph); sincos_small(s.theta, s.sth, s.cth); }
-  float sd_, cd_;
-  sincos_small(dpsi, sd_, cd_);                                 // yaw: rotate (sin, cos) by the increment
-  float ns = s.sps * cd_ + s.cps * sd_;
-  s.cps = s.cps * cd_ - s.sps * sd_;
-  s.sps = ns;
+  rotate_small(dphi, s.sph, s.cph);
+  rotate_small(dtheta, s.sth, s.cth);
+  rotate_small(dpsi, s.sps, s.cps);
   float u1 = s.cph * v1 - s.sph * v2, u2 = s.sph * v1 + s.cph * v2;      // Rx
   float r0 = s.cth * v0 + s.sth * u2, vw2 = s.cth * u2 - s.sth * v0;     // Ry
   s.vw0 = s.cps * r0 - s.sps * u1;                                       // Rz
@@ -289,6 +295,34 @@ SALP_HD void kin_step(const SalpDerived& dv, Motion32& s) {
   s.pw0 = fmaf(s.vw0, dt, s.pw0); s.pw1 = fmaf(s.vw1, dt, s.pw1); s.pw2 = fmaf(vw2, dt, s.pw2);
   s.pos0 = fmaf(v0, dt, s.pos0); s.pos1 = fmaf(v1, dt, s.pos1); s.pos2 = fmaf(v2, dt, s.pos2);
   s.ang0 = fmaf(w0, dt, s.ang0); s.ang1 = fmaf(w1, dt, s.ang1); s.ang2 = fmaf(w2, dt, s.ang2);
+}
+
+// (sin, cos) of an fp64 angle total, rounded to fp32: the chunk anchor.  Small angles (roll and
+// pitch, nearly always) take the fp32 path; the fp32 rounding of the ARGUMENT is < 6e-8 there.
+SALP_HD void anchor_sincos(double x, float& sn, float& cs) {
+  if (fabs(x) < 1.0) {
+    sincos32((float)x, sn, cs);
+  } else {
+    double s64, c64;
+    sincos(x, &s64, &c64);
+    sn = (float)s64;
+    cs = (float)c64;
+  }
+}
+
+// fold the fp32 chunk partials into the fp64 totals and re-anchor the three (sin, cos) pairs
+SALP_HD void flush_chunk(Body64& b, Motion32& s) {
+  b.pw[0] += (double)s.pw0; b.pw[1] += (double)s.pw1; b.pw[2] += (double)s.pw2;
+  b.pos[0] += (double)s.pos0; b.pos[1] += (double)s.pos1; b.pos[2] += (double)s.pos2;
+  b.ang[0] += (double)s.ang0; b.ang[1] += (double)s.ang1; b.ang[2] += (double)s.ang2;
+  b.eul[0] += (double)s.phi_lo; b.eul[1] += (double)s.theta_lo; b.eul[2] += (double)s.psi_lo;
+  anchor_sincos(b.eul[0], s.sph, s.cph);
+  anchor_sincos(b.eul[1], s.sth, s.cth);
+  anchor_sincos(b.eul[2], s.sps, s.cps);
+  s.phi_lo = s.theta_lo = s.psi_lo = 0.f;
+  s.pw0 = s.pw1 = s.pw2 = 0.f;
+  s.pos0 = s.pos1 = s.pos2 = 0.f;
+  s.ang0 = s.ang1 = s.ang2 = 0.f;
 }
 
 // Shape bookkeeping in fp64 (everything the reference differences) + the fp32 coefficient set.
@@ -370,17 +404,11 @@ SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDeriv
   s.w0 = (float)b.w[0]; s.w1 = (float)b.w[1]; s.w2 = (float)b.w[2];
   s.ac0 = (float)b.acc[0]; s.ac1 = (float)b.acc[1]; s.ac2 = (float)b.acc[2];
   s.al0 = (float)b.alp[0]; s.al1 = (float)b.alp[1]; s.al2 = (float)b.alp[2];
-  s.phi = (float)b.eul[0]; s.theta = (float)b.eul[1];
-  sincos32(s.phi, s.sph, s.cph);
-  sincos32(s.theta, s.sth, s.cth);
-  double psi64 = b.eul[2];
-  {
-    double sb64, cb64;
-    sincos(psi64, &sb64, &cb64);
-    s.sps = (float)sb64;
-    s.cps = (float)cb64;
-  }
-  s.psi_lo = 0.f; s.pw0 = s.pw1 = s.pw2 = 0.f;
+  anchor_sincos(b.eul[0], s.sph, s.cph);
+  anchor_sincos(b.eul[1], s.sth, s.cth);
+  anchor_sincos(b.eul[2], s.sps, s.cps);
+  s.phi_lo = s.theta_lo = s.psi_lo = 0.f;
+  s.pw0 = s.pw1 = s.pw2 = 0.f;
   s.pos0 = s.pos1 = s.pos2 = 0.f; s.ang0 = s.ang1 = s.ang2 = 0.f;
   s.vw0 = s.vw1 = 0.f;
 
@@ -403,41 +431,17 @@ SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDeriv
   int k = 1;
   while (k < K) {
     const int kend = k + SALP_MIXED_CHUNK < K ? k + SALP_MIXED_CHUNK : K;
-    // roll / pitch move by < 0.1 rad per chunk; beyond 0.45 rad the chunk takes the range-reduced path
-    if (!(fabsf(s.phi) >= 0.45f || fabsf(s.theta) >= 0.45f)) {     // (NaN counts as narrow: the env is being cut anyway)
-      for (; k < kend; k++) {
-        kin_step<false>(dv, s);
-        dyn_step(dv, g, s);
-        SALP_AFTER_SUBSTEP(k + 1)
-      }
-    } else {
-      for (; k < kend; k++) {
-        kin_step<true>(dv, s);
-        dyn_step(dv, g, s);
-        SALP_AFTER_SUBSTEP(k + 1)
-      }
+    for (; k < kend; k++) {
+      kin_step(dv, s);
+      dyn_step(dv, g, s);
+      SALP_AFTER_SUBSTEP(k + 1)
     }
-    // two-level sums: fold the fp32 chunk partials into the fp64 totals, re-anchor sin/cos(yaw)
-    b.pw[0] += (double)s.pw0; b.pw[1] += (double)s.pw1; b.pw[2] += (double)s.pw2;
-    b.pos[0] += (double)s.pos0; b.pos[1] += (double)s.pos1; b.pos[2] += (double)s.pos2;
-    b.ang[0] += (double)s.ang0; b.ang[1] += (double)s.ang1; b.ang[2] += (double)s.ang2;
-    psi64 += (double)s.psi_lo;
-    {
-      double sb64, cb64;
-      sincos(psi64, &sb64, &cb64);
-      s.sps = (float)sb64;
-      s.cps = (float)cb64;
-    }
-    s.psi_lo = 0.f; s.pw0 = s.pw1 = s.pw2 = 0.f;
-    s.pos0 = s.pos1 = s.pos2 = 0.f; s.ang0 = s.ang1 = s.ang2 = 0.f;
+    flush_chunk(b, s);       // two-level sums (fp32 chunk partials -> fp64 totals)
   }
 #undef SALP_AFTER_SUBSTEP
   // ---- the last substep's kinematic update ----
-  kin_step<true>(dv, s);
-  b.pw[0] += (double)s.pw0; b.pw[1] += (double)s.pw1; b.pw[2] += (double)s.pw2;
-  b.pos[0] += (double)s.pos0; b.pos[1] += (double)s.pos1; b.pos[2] += (double)s.pos2;
-  b.ang[0] += (double)s.ang0; b.ang[1] += (double)s.ang1; b.ang[2] += (double)s.ang2;
-  psi64 += (double)s.psi_lo;
+  kin_step(dv, s);
+  flush_chunk(b, s);
 
   // ---- epilogue: back to the carried fp64 columns ----
   if (st.last_update != K) {     // static tail: update_properties re-assigned the same shape (robot.py:651-668)
@@ -450,7 +454,6 @@ SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDeriv
   b.w[0] = s.w0; b.w[1] = s.w1; b.w[2] = s.w2;
   b.acc[0] = s.ac0; b.acc[1] = s.ac1; b.acc[2] = s.ac2;
   b.alp[0] = s.al0; b.alp[1] = s.al1; b.alp[2] = s.al2;
-  b.eul[0] = s.phi; b.eul[1] = s.theta; b.eul[2] = psi64;
   b.phase = phase_at(c, tK);
   b.length = p.init_length - st.dl;
   b.width = p.init_width + st.dl;

@@ -4,6 +4,21 @@
 #pragma once
 #include "salp_env.cuh"
 
+// Two register budgets of the same kernel: the throughput build (<= 128 registers, 16 warps/SM) for
+// batches that fill the GPU, and the latency build (<= 255 registers, used with one warp per
+// block) for small batches, where each SM sub-partition holds at most one warp and only
+// instruction-level parallelism inside that warp hides the FP32 pipe latency.
+template <int PREC>
+__global__ void __launch_bounds__(32, 1)
+salp_step_kernel_lat(const __grid_constant__ SalpParams p, const __grid_constant__ SalpDerived dv,
+                     const __grid_constant__ SalpView v, const __grid_constant__ SalpStepIO io, uint32_t flags,
+                     const int32_t* __restrict__ order) {
+  int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= v.n) return;
+  int64_t i = order ? (int64_t)order[tid] : tid;
+  env_step<PREC>(p, dv, v, io, flags, i);
+}
+
 template <int PREC>
 __global__ void __launch_bounds__(128, 4)
 salp_step_kernel(const __grid_constant__ SalpParams p, const __grid_constant__ SalpDerived dv,
