@@ -225,7 +225,7 @@ int salp_create(const SalpParams* params, int64_t num_envs, int device, uint64_t
   v.time_table = table;
   ALLOC(h->scratch.K, sizeof(int32_t) * n);
   ALLOC(h->scratch.order, sizeof(int32_t) * n);
-  ALLOC(h->scratch.hist, sizeof(int32_t) * (SALP_MAX_SUBSTEPS + 2));
+  ALLOC(h->scratch.hist, sizeof(int32_t) * SALP_SORT_BINS);
   ALLOC(h->d_actions, sizeof(float) * 3 * n);
   ALLOC(h->d_obs, sizeof(float) * D * n);
   ALLOC(h->d_reward, sizeof(float) * n);

@@ -15,6 +15,8 @@
 #include "../../include/salp_b200.h"
 
 #define SALP_MAX_SUBSTEPS 4096          // cycles longer than this raise SALP_ERR_RANGE (Box actions: K <= 1348)
+#define SALP_SORT_SHAPE_BINS 64          // K-sort key = (K >> 5) * 64 + min(end of shape motion >> 3, 63)
+#define SALP_SORT_BINS (((SALP_MAX_SUBSTEPS >> 5) + 1) * SALP_SORT_SHAPE_BINS)
 #define SALP_NUM_F32 (SALP_F32_END - SALP_F32_BASE)
 #define SALP_NUM_I32 (SALP_I32_END - SALP_I32_BASE)
 
@@ -40,9 +42,9 @@ struct SalpView {
 
 // Per-step scratch owned by the handle (K-sort path).
 struct SalpScratch {
-  int32_t* K;           // [n]   substep count of the pending cycle
+  int32_t* K;           // [n]   sort key of the pending cycle (K bucket, end of shape motion)
   int32_t* order;       // [n]   env indices sorted by K (descending)
-  int32_t* hist;        // [SALP_MAX_SUBSTEPS + 2] counting-sort histogram / offsets
+  int32_t* hist;        // [SALP_SORT_BINS] counting-sort histogram / offsets
 };
 
 // Launchers implemented in salp_kernels.cu (all asynchronous on `stream`).

@@ -266,3 +266,45 @@ SALP_DEV int plan_substeps(const CyclePlan& c, const double* time_table) {
   }
   return lo;
 }
+
+// first k in [0, SALP_MAX_SUBSTEPS] with !(t_k < x) (strict) or !(t_k <= x) (non-strict); the
+// guess x/dt is within one or two entries of the answer, so this is a couple of table reads.
+template <bool STRICT>
+SALP_DEV int first_k_past(const double* table, double x, double inv_dt) {
+  if (!(x == x)) return 0;                                         // NaN: every comparison is False
+  double g = x * inv_dt;
+  int k = g < 0.0 ? 0 : (g > (double)SALP_MAX_SUBSTEPS ? SALP_MAX_SUBSTEPS : (int)g);
+  while (k > 0 && !(STRICT ? table[k - 1] < x : table[k - 1] <= x)) k--;
+  while (k < SALP_MAX_SUBSTEPS && (STRICT ? table[k] < x : table[k] <= x)) k++;
+  return k;
+}
+
+
+// Integer phase plan of one cycle (robot.py:640-649 evaluated on the table t_j; update j follows
+// substep j-1):  phase_j = 0 for j < k_T0, 1 for k_T0 <= j < k_jet, 2/3 afterwards.  The body
+// shape moves at updates j <= k_ref (refill ramp and its end) and k_T0 <= j <= k_jet (jet and its
+// end); two more updates flush the first/second backward differences.
+struct PhasePlan {
+  int k_ref, k_T0, k_jet;
+  int upd_a_end, upd_b_begin, upd_b_end;
+};
+SALP_DEV PhasePlan make_phase_plan(const CyclePlan& c, const double* time_table, double inv_dt) {
+  PhasePlan pp;
+  pp.k_ref = first_k_past<true>(time_table, c.refill, inv_dt);
+  pp.k_T0 = first_k_past<false>(time_table, c.T0, inv_dt);
+  pp.k_jet = first_k_past<false>(time_table, c.Tjet, inv_dt);
+  pp.upd_a_end = (pp.k_ref > 1 ? pp.k_ref : 1) + 2;
+  pp.upd_b_begin = pp.k_T0;
+  pp.upd_b_end = (pp.k_jet > pp.k_T0 ? pp.k_jet : pp.k_T0) + 2;
+  return pp;
+}
+
+// Sort key of the K-sort: coarse K bucket (32 substeps) first, then the end of the shape motion
+// (8-substep bins, capped), so that the lanes of a warp both finish together AND leave the
+// shape-update window together.
+SALP_DEV int sort_key(int K, const PhasePlan& pp) {
+  int e = pp.upd_b_end < K ? pp.upd_b_end : K;
+  e = e >> 3;
+  e = e < SALP_SORT_SHAPE_BINS - 1 ? e : SALP_SORT_SHAPE_BINS - 1;
+  return (K >> 5) * SALP_SORT_SHAPE_BINS + e;
+}

@@ -21,7 +21,7 @@ __global__ void salp_reset_kernel(const __grid_constant__ SalpParams p, const __
 
 // ---- K-sort: balance warps by substep count (SURVEY.md hard part 3) ----------------------------
 // salp_plan_kernel recomputes the cycle plan of every env (cheap: one inverse-kinematics solve)
-// and histograms K; salp_scan_kernel turns the histogram into descending-K offsets;
+// and histograms the sort key (K bucket, end of shape motion); salp_scan_kernel turns the histogram into descending-K offsets;
 // salp_scatter_kernel writes the env permutation.  The step kernel then walks `order`.
 __global__ void salp_plan_kernel(const __grid_constant__ SalpParams p, const __grid_constant__ SalpView v,
                                  const float* __restrict__ actions, int32_t* __restrict__ Kout,
@@ -33,14 +33,15 @@ __global__ void salp_plan_kernel(const __grid_constant__ SalpParams p, const __g
                                    c.d(SALP_F_NOZZLE_ANGLE1), c.d(SALP_F_NOZZLE_ANGLE2));
   int K = plan_substeps(plan, v.time_table);
   K = K < 0 ? SALP_MAX_SUBSTEPS : K;
-  Kout[i] = K;
-  atomicAdd(&hist[K], 1);
+  const int key = sort_key(K, make_phase_plan(plan, v.time_table, 1.0 / p.dt));
+  Kout[i] = key;
+  atomicAdd(&hist[key], 1);
 }
 
-// one block of 1024 threads; bins 0..SALP_MAX_SUBSTEPS; offsets for DESCENDING K (long cycles first)
+// one block of 1024 threads; bins 0..SALP_SORT_BINS-1; offsets for DESCENDING key (long cycles first)
 __global__ void salp_scan_kernel(int32_t* __restrict__ hist) {
   __shared__ int32_t part[1024];
-  constexpr int NB = SALP_MAX_SUBSTEPS + 1;
+  constexpr int NB = SALP_SORT_BINS;
   constexpr int PER = (NB + 1023) / 1024;
   int tid = threadIdx.x;
   int32_t local[PER];
@@ -99,7 +100,7 @@ int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& i
   int launches = 0;
   const int32_t* order = nullptr;
   if (flags & SALP_STEP_SORT_BY_K) {
-    if (cudaMemsetAsync(scratch.hist, 0, sizeof(int32_t) * (SALP_MAX_SUBSTEPS + 2), stream) != cudaSuccess)
+    if (cudaMemsetAsync(scratch.hist, 0, sizeof(int32_t) * SALP_SORT_BINS, stream) != cudaSuccess)
       return SALP_ERR_CUDA;
     salp_plan_kernel<<<grid_for(v.n, 128), 128, 0, stream>>>(p, v, io.actions, scratch.K, scratch.hist);
     salp_scan_kernel<<<1, 1024, 0, stream>>>(scratch.hist);

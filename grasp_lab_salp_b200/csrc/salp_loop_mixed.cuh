@@ -81,6 +81,7 @@ struct SalpDerived {
   double inv_dt, four_thirds_pi, skin3, c2, c1, c0, comA, comB, mtot0, m0, jet_gain;
   // fp32
   float dt, ratio_f, pi, end_aspect, inv_aspect_span, half_rho_neg, torque_ratio, arm0;
+  float init_length_f, init_width_f, jet_gain_f, rho_f, m_base_f, four_thirds_pi_f, skin3_f, c2_f, c1_f, c0_f;   // fp32 shape (never differenced)
   float Ca[3], E[3], Cat[3], Car[3], CaD[3], CatF[3];
   float thi[3], tspan[3], rhi[3], rspan[3];
 };
@@ -108,6 +109,16 @@ SALP_HD SalpDerived make_derived(const SalpParams& p) {
   k.m0 = p.dry_mass + nm;
   // F_jet = -Cd * mass_rate * (dV/dt / A_nozzle) * dir,  mass_rate = rho dV/dt   (dynamics.py:88-101)
   k.jet_gain = -p.discharge_coefficient * p.density / p.nozzle_area;
+  k.init_length_f = (float)p.init_length;
+  k.init_width_f = (float)p.init_width;
+  k.jet_gain_f = (float)k.jet_gain;
+  k.rho_f = (float)p.density;
+  k.m_base_f = (float)(p.dry_mass + nm - p.density * p.tube_volume);    // m = dry + nozzle + rho (V_ell - V_tube)
+  k.four_thirds_pi_f = (float)k.four_thirds_pi;
+  k.skin3_f = (float)k.skin3;
+  k.c2_f = (float)k.c2;
+  k.c1_f = (float)k.c1;
+  k.c0_f = (float)k.c0;
   k.dt = (float)p.dt;
   k.ratio_f = (float)p.drag_force_ratio;
   k.pi = (float)M_PI;
@@ -175,23 +186,32 @@ SALP_HD void shape64_at(const SalpParams& p, const SalpDerived& k, double lh, do
   com = (k.comA * lh + k.comB) / (k.mtot0 + wm);
 }
 
-// All fp32 coefficients of the coming substep from the fp64 shape results.
-SALP_HD void make_coefs(const SalpDerived& k, const float dir[3], bool jet_on, float lh, float wh, float m,
-                        float I0, float I1, float I_rate0, float I_rate1, float mass_rate, float dV_dt,
-                        float com, float com_rate, float com_acc, Coef32& g) {
+// All fp32 coefficients of the coming substep.  Mass, inertia, areas and drag coefficients are
+// evaluated in fp32 from the half-length / half-width (they are never differenced); the
+// differenced quantities arrive from the fp64 chain already rounded.
+SALP_HD void make_coefs(const SalpDerived& k, const float dir[3], bool jet_on, float lh, float wh,
+                        float I_rate0, float I_rate1, float dV_dt, float com, float com_rate, float com_acc,
+                        Coef32& g) {
+  const float wh2 = wh * wh, lh2 = lh * lh;
+  const float Ve = k.four_thirds_pi_f * lh * wh2;                  // geometry.py:79-81
+  const float m = fmaf(k.rho_f, Ve, k.m_base_f);                   // robot.py:1055-1063
+  const float sw = fmaf(200.0f, Ve, k.skin3_f);                    // geometry.py:134-183
+  const float I0 = sw * (wh2 + wh2);
+  const float I1 = fmaf(k.c2_f, lh2, fmaf(k.c1_f, lh, k.c0_f)) + sw * (lh2 + wh2);
   const float inv_m = fast_rcp(m);
   const float inv_I0 = fast_rcp(I0), inv_I1 = fast_rcp(I1);
-  const float a0 = k.pi * wh * wh, a1 = k.pi * lh * wh;          // geometry.py:68-75
+  const float a0 = k.pi * wh2, a1 = k.pi * lh * wh;                // geometry.py:68-75
   float nr = (lh * fast_rcp(wh) - k.end_aspect) * k.inv_aspect_span;   // geometry.py:105-123
   nr = fminf(fmaxf(nr, 0.0f), 1.0f);
   const float width = wh + wh;
-  const float w3 = width * width * width, l3 = 8.0f * lh * lh * lh;
+  const float w3 = width * width * width, l3 = 8.0f * lh * lh2;
   const float area[3] = {a0, a1, a1};
   const float dims[3] = {w3, l3, l3};
   const float I[3] = {I0, I1, I1};
   const float inv_I[3] = {inv_I0, inv_I1, inv_I1};
   const float I_rate[3] = {I_rate0, I_rate1, I_rate1};
-  const float f = jet_on ? (float)k.jet_gain * dV_dt * dV_dt : 0.0f;
+  const float f = jet_on ? k.jet_gain_f * dV_dt * dV_dt : 0.0f;
+  const float mass_rate = k.rho_f * dV_dt;                         // geometry.py:98-101
   const float armx = k.arm0 - lh;
 #pragma unroll
   for (int i = 0; i < 3; i++) {
@@ -212,18 +232,6 @@ SALP_HD void make_coefs(const SalpDerived& k, const float dir[3], bool jet_on, f
   g.com = com;
   g.com_rate = com_rate;
   g.com_acc = com_acc;
-}
-
-// first k in [0, SALP_MAX_SUBSTEPS] with !(t_k < x) (strict) or !(t_k <= x) (non-strict); the
-// guess x/dt is within one or two entries of the answer, so this is a couple of table reads.
-template <bool STRICT>
-SALP_HD int first_k_past(const double* table, double x, double inv_dt) {
-  if (!(x == x)) return 0;                                         // NaN: every comparison is False
-  double g = x * inv_dt;
-  int k = g < 0.0 ? 0 : (g > (double)SALP_MAX_SUBSTEPS ? SALP_MAX_SUBSTEPS : (int)g);
-  while (k > 0 && !(STRICT ? table[k - 1] < x : table[k - 1] <= x)) k--;
-  while (k < SALP_MAX_SUBSTEPS && (STRICT ? table[k] < x : table[k] <= x)) k++;
-  return k;
 }
 
 // fp32 register state of one env inside the substep loop
@@ -346,9 +354,10 @@ SALP_HD void shape_update(const SalpParams& p, const SalpDerived& dv, const Cycl
   double com_rate = (com - st.s.com) * dv.inv_dt;                // robot.py:901-910
   st.com_acc = (com_rate - st.prev_com_rate) * dv.inv_dt;        // robot.py:912-922
   st.prev_com_rate = com_rate;
-  make_coefs(dv, dir, phase == 1, (float)lh, (float)wh, (float)(dv.m0 + wm), (float)I0n, (float)I1n,
+  const float dl32 = (float)st.dl;
+  make_coefs(dv, dir, phase == 1, 0.5f * (dv.init_length_f - dl32), 0.5f * (dv.init_width_f + dl32),
              (float)((I0n - st.s.I0) * dv.inv_dt), (float)((I1n - st.s.I1) * dv.inv_dt),
-             (float)(p.density * dV_dt), (float)dV_dt, (float)com, (float)com_rate, (float)st.com_acc, g);
+             (float)dV_dt, (float)com, (float)com_rate, (float)st.com_acc, g);
   st.prevV = st.s.V;
   st.I0_prev_used = st.s.I0;
   st.I1_prev_used = st.s.I1;
@@ -368,12 +377,9 @@ SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDeriv
   //   phase_j = 0 for j < k_T0, 1 for k_T0 <= j < k_jet, 2/3 afterwards
   //   the shape moves at updates j <= k_ref (refill ramp and its end) and k_T0 <= j <= k_jet (jet
   //   and its end); two more updates flush the first/second backward differences
-  const int k_ref = first_k_past<true>(time_table, c.refill, dv.inv_dt);
-  const int k_T0 = first_k_past<false>(time_table, c.T0, dv.inv_dt);
-  const int k_jet = first_k_past<false>(time_table, c.Tjet, dv.inv_dt);
-  const int upd_a_end = (k_ref > 1 ? k_ref : 1) + 2;
-  const int upd_b_begin = k_T0;
-  const int upd_b_end = (k_jet > k_T0 ? k_jet : k_T0) + 2;
+  const PhasePlan pp = make_phase_plan(c, time_table, dv.inv_dt);
+  const int k_T0 = pp.k_T0, k_jet = pp.k_jet;
+  const int upd_a_end = pp.upd_a_end, upd_b_begin = pp.upd_b_begin, upd_b_end = pp.upd_b_end;
   const float dir[3] = {(float)c.dir[0], (float)c.dir[1], (float)c.dir[2]};
 
   // ---- prologue: shape-derived state of the first substep from the carried columns ----
@@ -391,9 +397,9 @@ SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDeriv
     // the carried centre of mass may be stale w.r.t. length/width (Robot.reset quirk, robot.py:478)
     st.s.com = b.com;
     st.s.com_rate = b.com_rate;
-    make_coefs(dv, dir, b.phase == 1, (float)lh, (float)wh, (float)(dv.m0 + wm), (float)st.s.I0, (float)st.s.I1,
+    make_coefs(dv, dir, b.phase == 1, (float)lh, (float)wh,
                (float)((st.s.I0 - b.prevI[0]) * dv.inv_dt), (float)((st.s.I1 - b.prevI[1]) * dv.inv_dt),
-               (float)(p.density * dV_dt), (float)dV_dt, (float)b.com, (float)b.com_rate, (float)b.com_acc, g);
+               (float)dV_dt, (float)b.com, (float)b.com_rate, (float)b.com_acc, g);
     st.I0_prev_used = st.s.I0;
     st.I1_prev_used = st.s.I1;
   }

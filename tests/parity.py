@@ -35,6 +35,7 @@ STATE_MAP = {
 # near-zero channels (out-of-plane motion, SURVEY.md hard part 5): compared with an absolute floor
 SMALL_CHANNELS = {"posw_z", "vel_z", "euler_x", "euler_y", "angvel_x", "angvel_y", "pos_z", "angle_x",
                   "angle_y", "acc_z", "angacc_x", "angacc_y"}
+ANGLE_CHANNELS = {"euler_z", "angle_z"}
 METRIC_COLS = {"path_length": 2, "direct_distance": 3, "path_efficiency": 4, "final_distance": 5,
                "initial_distance": 6, "avg_compression": 7, "avg_coast_time": 8, "avg_nozzle_angle": 9,
                "avg_velocity": 10, "avg_rewards_track": 11, "avg_rewards_heading": 12,
@@ -61,8 +62,8 @@ def rel_err(a, b, floor):
 #  * F64 ("reference mode", and the C oracle): same float64 algorithm, different libm / summation
 #    order -> 1e-9 relative.
 #  * MIXED (fp32 motion state): the north-star tolerance, 1e-5 relative per step on position,
-#    velocity, heading, body shape -- relative to max(|ref|, 0.1) (0.1 m, 0.1 m/s, 0.1 rad: the
-#    scale of one cycle's motion; a pure relative test is meaningless for a coordinate that
+#    velocity, heading, body shape -- relative to max(|ref|, 0.1) (0.1 m, 0.1 m/s: the scale of
+#    one cycle's motion; yaw relative to max(|ref|, 1 rad); a pure relative test is meaningless for a coordinate that
 #    happens to cross zero).  Rewards carry the reference's own x100 gain on distances
 #    (salp_robot_env.py:352), hence floor 10.  Accelerations are not in the north-star list and
 #    are sums of cancelling forces: 1e-4.
@@ -112,6 +113,8 @@ def replay_golden(backend, g, rtol, *, small_rtol=None, small_floor=1e-7, floor=
             ref = g["state"][:, t, j]
             got = backend.get_state(col)
             fl = small_floor if nm in SMALL_CHANNELS else floor
+            if nm in ANGLE_CHANNELS and floor >= 0.1:
+                fl = max(fl, 1.0)
             tol = (small_rtol or rtol) if nm in SMALL_CHANNELS else rtol
             if nm.startswith(("acc_", "angacc_")):
                 # accelerations are finite-difference driven (differences of O(1) numbers / dt):
@@ -244,6 +247,8 @@ def lockstep_compare(product, oracle, actions, *, resync, rtol, floor, reward_fl
             # out-of-plane channels are excited only by rounding-level asymmetries (nozzle direction
             # z ~ 2e-16): they are noise-driven and compared against an absolute floor
             fl = max(floor, small_floor or 1e-4) if col in SMALL_CHANNELS else floor
+            if col in ANGLE_CHANNELS and floor >= 0.1:
+                fl = max(fl, 1.0)       # an angle is relative to 1 rad, not to how close to 0 it happens to end
             e = rel_err(got[ok], ref[ok], fl)
             errs[col] = float(e.max()) if e.size else 0.0
         rew_o64, rew_p64 = oracle.terms[:, 7], product.terms[:, 7]      # float64 totals (io.reward is float32)
