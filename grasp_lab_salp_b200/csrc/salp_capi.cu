@@ -207,6 +207,7 @@ int salp_create(const SalpParams* params, int64_t num_envs, int device, uint64_t
   v.n = n;
   v.env_id_offset = env_id_offset;
   v.seed = seed;
+  v.sm_count = prop.multiProcessorCount;
   double* table = nullptr;
 #define ALLOC(ptr, bytes)                                                                   \
   do {                                                                                      \

@@ -38,6 +38,7 @@ struct SalpView {
   int64_t pool_P;
   int32_t* status;      // sticky device status word (0 = ok)
   const double* time_table;   // t_k, k = 0..SALP_MAX_SUBSTEPS: k-fold repeated `+= dt` (robot.py:674)
+  int32_t sm_count;           // SMs of the handle's device (kernel selection)
 };
 
 // Per-step scratch owned by the handle (K-sort path).

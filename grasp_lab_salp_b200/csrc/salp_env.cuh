@@ -229,37 +229,58 @@ SALP_HD void store_body(const Cols& c, const Body64& b) {
   c.d(SALP_F_SPEED_WORLD) = b.speed_world;
 }
 
-// SalpRobotEnv.step (salp_robot_env.py:196-299) for env i.
-template <int PREC>
-SALP_HD void env_step(const SalpParams& p, const SalpDerived& dv, const SalpView& v, const SalpStepIO& io,
-                      uint32_t flags, int64_t i) {
+// ---- SalpRobotEnv.step (salp_robot_env.py:196-299) for env i, in three parts so that the fused
+// kernels (one thread does everything) and the warp-specialised pipeline kernel (three warps
+// share one env group, salp_pipe_kernel.cuh) run the same code:
+//   env_step_begin : reads only  -- action rescale, nozzle IK, set_control, state load
+//   run_cycle<PREC>              -- the K-substep loop (or the pipeline)
+//   env_step_end   : all writes  -- state store, reward, obs, termination, bookkeeping, auto-reset
+struct StepCtx {
+  float a0, a1, a2;
+  CyclePlan plan;
+  double avg_vy, avg_wz;      // lag-by-one cycle averages (robot.py:744-745)
+  double last_x, last_y;      // episode_positions[-1]
+  int cycle;
+};
+
+SALP_HD void env_step_begin(const SalpParams& p, const SalpView& v, const SalpStepIO& io, int64_t i, StepCtx& cx,
+                            Body64& b) {
+  Cols c{v, i};
+  cx.a0 = io.actions[3 * i];
+  cx.a1 = io.actions[3 * i + 1];
+  cx.a2 = io.actions[3 * i + 2];
+  // :201-209  rescale, Nozzle.set_yaw_angle / solve_angles, Robot.set_control
+  cx.plan = make_cycle_plan(p, cx.a0, cx.a1, cx.a2, c.d(SALP_F_NOZZLE_ANGLE1), c.d(SALP_F_NOZZLE_ANGLE2));
+  cx.cycle = c.n(SALP_F_CYCLE) + 1;
+  // :210  Robot.step_through_cycle (robot.py:740-757)
+  load_body(c, b);
+  const double tot = cx.plan.total64;
+  // lag-by-one: displacement of the PREVIOUS cycle over the NEW total (robot.py:744-748)
+  cx.avg_vy = (b.pos[1] - c.d(SALP_F_PREVPOS_Y)) / tot;
+  cx.avg_wz = (b.ang[2] - c.d(SALP_F_PREVANGLE_Z)) / tot;
+  cx.last_x = b.pw[0];
+  cx.last_y = b.pw[1];
+}
+
+// `pos0` / `ang0`: body-frame integrals at the START of the cycle (they become prev_position /
+// prev_angle, robot.py:747-748); K, t: substeps run and cycle_time reached.
+SALP_HD void env_step_end(const SalpParams& p, const SalpView& v, const SalpStepIO& io, uint32_t flags, int64_t i,
+                          const StepCtx& cx, const double pos0[3], const double ang0[3], Body64& b, int K, double t) {
   Cols c{v, i};
   const int D = SALP_OBS_BASE + 2 * p.num_obstacles;
-  const float a0 = io.actions[3 * i], a1 = io.actions[3 * i + 1], a2 = io.actions[3 * i + 2];
-
-  // :201-209  rescale, Nozzle.set_yaw_angle / solve_angles, Robot.set_control
-  CyclePlan plan = make_cycle_plan(p, a0, a1, a2, c.d(SALP_F_NOZZLE_ANGLE1), c.d(SALP_F_NOZZLE_ANGLE2));
+  const CyclePlan& plan = cx.plan;
+  const float a0 = cx.a0, a1 = cx.a1, a2 = cx.a2;
+  const double avg_vy = cx.avg_vy, avg_wz = cx.avg_wz, last_x = cx.last_x, last_y = cx.last_y;
+  const int cycle = cx.cycle;
   c.f(SALP_F_NOZZLE_YAW) = plan.yaw32;
   c.d(SALP_F_NOZZLE_ANGLE1) = plan.angle1;
   c.d(SALP_F_NOZZLE_ANGLE2) = plan.angle2;
-  const int cycle = c.n(SALP_F_CYCLE) + 1;
   c.n(SALP_F_CYCLE) = cycle;
-
-  // :210  Robot.step_through_cycle (robot.py:740-757)
-  Body64 b;
-  load_body(c, b);
-  const double tot = plan.total64;
-  // lag-by-one: displacement of the PREVIOUS cycle over the NEW total (robot.py:744-748)
-  const double avg_vy = (b.pos[1] - c.d(SALP_F_PREVPOS_Y)) / tot;
-  const double avg_wz = (b.ang[2] - c.d(SALP_F_PREVANGLE_Z)) / tot;
 #pragma unroll
   for (int k = 0; k < 3; k++) {
-    c.d(SALP_F_PREVPOS_X + k) = b.pos[k];
-    c.d(SALP_F_PREVANGLE_X + k) = b.ang[k];
+    c.d(SALP_F_PREVPOS_X + k) = pos0[k];
+    c.d(SALP_F_PREVANGLE_X + k) = ang0[k];
   }
-  const double last_x = b.pw[0], last_y = b.pw[1];     // episode_positions[-1]
-  double t = 0.0;
-  const int K = run_cycle<PREC>(p, dv, plan, v.time_table, b, t);
   if (K < 0) raise_status(v, SALP_ERR_RANGE);
   store_body(c, b);
 
@@ -371,4 +392,17 @@ SALP_HD void env_step(const SalpParams& p, const SalpDerived& dv, const SalpView
     for (int k = 0; k < D; k++) io.terminal_obs[i * D + k] = obs[k];
   // SB3 VecEnv worker semantics: reset the finished env, hand back the post-reset observation
   if ((flags & SALP_STEP_AUTORESET) && ended) env_reset(p, v, i, obs);
+}
+
+template <int PREC>
+SALP_HD void env_step(const SalpParams& p, const SalpDerived& dv, const SalpView& v, const SalpStepIO& io,
+                      uint32_t flags, int64_t i) {
+  StepCtx cx;
+  Body64 b;
+  env_step_begin(p, v, io, i, cx, b);
+  const double pos0[3] = {b.pos[0], b.pos[1], b.pos[2]};
+  const double ang0[3] = {b.ang[0], b.ang[1], b.ang[2]};
+  double t = 0.0;
+  const int K = run_cycle<PREC>(p, dv, cx.plan, v.time_table, b, t);
+  env_step_end(p, v, io, flags, i, cx, pos0, ang0, b, K, t);
 }

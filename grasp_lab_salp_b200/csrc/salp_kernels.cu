@@ -4,6 +4,7 @@
 // of an env in registers.  Kernel arguments (SalpParams, SalpView, SalpStepIO) are
 // __grid_constant__: they sit in the constant bank and every access is a uniform c[][] operand.
 #include "salp_step_kernel.cuh"
+#include "salp_pipe_kernel.cuh"
 
 __global__ void salp_init_kernel(const __grid_constant__ SalpParams p, const __grid_constant__ SalpView v) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -110,6 +111,20 @@ int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& i
     order = scratch.order;
   }
   const int block = block_for(v.n);
+  // small batches that fit one wave of 32-env blocks: the warp-specialised pipeline
+  if (p.precision == SALP_PRECISION_MIXED && !order && !(flags & SALP_STEP_NO_PIPELINE) &&
+      v.n <= (int64_t)32 * (v.sm_count > 0 ? v.sm_count : 148)) {
+    static bool configured = false;
+    if (!configured) {
+      if (cudaFuncSetAttribute(salp_step_kernel_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)sizeof(PipeShared)) != cudaSuccess)
+        return SALP_ERR_CUDA;
+      configured = true;
+    }
+    salp_step_kernel_pipe<<<grid_for(v.n, 32), SALP_PIPE_THREADS, sizeof(PipeShared), stream>>>(p, make_derived(p), v, io, flags);
+    SALP_LAUNCH_CHECK();
+    return launches + 1;
+  }
   if (p.precision == SALP_PRECISION_F64)
     salp_launch_step_f64(p, v, io, flags, order, stream);     // salp_step_f64.cu (compiled with -fmad=false)
   else if (block == 32)

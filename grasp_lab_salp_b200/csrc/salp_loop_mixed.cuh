@@ -365,51 +365,34 @@ SALP_HD void shape_update(const SalpParams& p, const SalpDerived& dv, const Cycl
   st.last_update = j;
 }
 
-template <>
-SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c,
-                                            const double* time_table, Body64& b, double& t_out) {
-  // ---- K: first k with !(t_k < total) in the dtype the reference compares in (robot.py:756) ----
-  const int K = plan_substeps(c, time_table);
-  t_out = 0.0;
-  if (K <= 0) return K;            // K == 0: nothing moves; K < 0: range error (non-finite action)
-
-  // ---- integer phase plan (robot.py:640-649 on the table t_j; update j follows substep j-1) ----
-  //   phase_j = 0 for j < k_T0, 1 for k_T0 <= j < k_jet, 2/3 afterwards
-  //   the shape moves at updates j <= k_ref (refill ramp and its end) and k_T0 <= j <= k_jet (jet
-  //   and its end); two more updates flush the first/second backward differences
-  const PhasePlan pp = make_phase_plan(c, time_table, dv.inv_dt);
-  const int k_T0 = pp.k_T0, k_jet = pp.k_jet;
-  const int upd_a_end = pp.upd_a_end, upd_b_begin = pp.upd_b_begin, upd_b_end = pp.upd_b_end;
-  const float dir[3] = {(float)c.dir[0], (float)c.dir[1], (float)c.dir[2]};
-
-  // ---- prologue: shape-derived state of the first substep from the carried columns ----
-  ShapeTrack st;
-  Coef32 g;
+// ---- building blocks shared by the fused loop below and the pipeline kernel ------------------
+// shape-derived state of the first substep (coefficient set g_0) from the carried columns
+SALP_HD void mixed_init_shape(const SalpParams& p, const SalpDerived& dv, const Body64& b, const float dir[3],
+                              ShapeTrack& st, Coef32& g) {
   st.prev_com_rate = b.prev_com_rate;
   st.com_acc = b.com_acc;
   st.prevV = b.prev_volume;
-  st.dl = 0.0;
+  st.dl = p.init_length - b.length;
   st.last_update = 0;
-  {
-    double lh = 0.5 * b.length, wh = 0.5 * b.width, wm, com_now;
-    shape64_at(p, dv, lh, wh, st.s.V, st.s.I0, st.s.I1, com_now, wm);
-    double dV_dt = (st.s.V - b.prev_volume) * dv.inv_dt;
-    // the carried centre of mass may be stale w.r.t. length/width (Robot.reset quirk, robot.py:478)
-    st.s.com = b.com;
-    st.s.com_rate = b.com_rate;
-    make_coefs(dv, dir, b.phase == 1, (float)lh, (float)wh,
-               (float)((st.s.I0 - b.prevI[0]) * dv.inv_dt), (float)((st.s.I1 - b.prevI[1]) * dv.inv_dt),
-               (float)dV_dt, (float)b.com, (float)b.com_rate, (float)b.com_acc, g);
-    st.I0_prev_used = st.s.I0;
-    st.I1_prev_used = st.s.I1;
-  }
-
-  // ---- fp32 motion state ----
-  Motion32 s;
+  double lh = 0.5 * b.length, wh = 0.5 * b.width, wm, com_now;
+  shape64_at(p, dv, lh, wh, st.s.V, st.s.I0, st.s.I1, com_now, wm);
+  double dV_dt = (st.s.V - b.prev_volume) * dv.inv_dt;
+  // the carried centre of mass may be stale w.r.t. length/width (Robot.reset quirk, robot.py:478)
+  st.s.com = b.com;
+  st.s.com_rate = b.com_rate;
+  make_coefs(dv, dir, b.phase == 1, (float)lh, (float)wh,
+             (float)((st.s.I0 - b.prevI[0]) * dv.inv_dt), (float)((st.s.I1 - b.prevI[1]) * dv.inv_dt),
+             (float)dV_dt, (float)b.com, (float)b.com_rate, (float)b.com_acc, g);
+  st.I0_prev_used = st.s.I0;
+  st.I1_prev_used = st.s.I1;
+}
+SALP_HD void mixed_init_dyn(const Body64& b, Motion32& s) {
   s.v0 = (float)b.v[0]; s.v1 = (float)b.v[1]; s.v2 = (float)b.v[2];
   s.w0 = (float)b.w[0]; s.w1 = (float)b.w[1]; s.w2 = (float)b.w[2];
   s.ac0 = (float)b.acc[0]; s.ac1 = (float)b.acc[1]; s.ac2 = (float)b.acc[2];
   s.al0 = (float)b.alp[0]; s.al1 = (float)b.alp[1]; s.al2 = (float)b.alp[2];
+}
+SALP_HD void mixed_init_kin(const Body64& b, Motion32& s) {
   anchor_sincos(b.eul[0], s.sph, s.cph);
   anchor_sincos(b.eul[1], s.sth, s.cth);
   anchor_sincos(b.eul[2], s.sps, s.cps);
@@ -417,50 +400,14 @@ SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDeriv
   s.pw0 = s.pw1 = s.pw2 = 0.f;
   s.pos0 = s.pos1 = s.pos2 = 0.f; s.ang0 = s.ang1 = s.ang2 = 0.f;
   s.vw0 = s.vw1 = 0.f;
-
-  // The kinematic update of substep k-1 only READS the (v, w) that the dynamics of substep k also
-  // only reads, so the loop runs kin(k-1) side by side with dyn(k): two independent dependency
-  // chains per iteration instead of one long one.  Substep 0's dynamics is peeled off in front,
-  // substep K-1's kinematics behind.
-  int next_upd;                     // next update index j at which the shape (or its differences) moves
-  dyn_step(dv, g, s);
-  shape_update(p, dv, c, time_table, dir, 1, k_T0, k_jet, st, g);
-  next_upd = 2;
-
-#define SALP_AFTER_SUBSTEP(j)                                                                   \
-  if ((j) == next_upd) {                                                                        \
-    shape_update(p, dv, c, time_table, dir, (j), k_T0, k_jet, st, g);                           \
-    next_upd = ((j) < upd_a_end || ((j) >= upd_b_begin && (j) < upd_b_end)) ? (j) + 1           \
-               : ((j) < upd_b_begin ? upd_b_begin : 0x7fffffff);                                \
-  }
-
-  int k = 1;
-  while (k < K) {
-    const int kend = k + SALP_MIXED_CHUNK < K ? k + SALP_MIXED_CHUNK : K;
-    for (; k < kend; k++) {
-      kin_step(dv, s);
-      dyn_step(dv, g, s);
-      SALP_AFTER_SUBSTEP(k + 1)
-    }
-    flush_chunk(b, s);       // two-level sums (fp32 chunk partials -> fp64 totals)
-  }
-#undef SALP_AFTER_SUBSTEP
-  // ---- the last substep's kinematic update ----
-  kin_step(dv, s);
-  flush_chunk(b, s);
-
-  // ---- epilogue: back to the carried fp64 columns ----
+}
+// back to the carried fp64 columns
+SALP_HD void mixed_finish_shape(const SalpParams& p, ShapeTrack& st, int K, Body64& b) {
   if (st.last_update != K) {     // static tail: update_properties re-assigned the same shape (robot.py:651-668)
     st.prevV = st.s.V;
     st.I0_prev_used = st.s.I0;
     st.I1_prev_used = st.s.I1;
   }
-  const double tK = time_table[K];
-  b.v[0] = s.v0; b.v[1] = s.v1; b.v[2] = s.v2;
-  b.w[0] = s.w0; b.w[1] = s.w1; b.w[2] = s.w2;
-  b.acc[0] = s.ac0; b.acc[1] = s.ac1; b.acc[2] = s.ac2;
-  b.alp[0] = s.al0; b.alp[1] = s.al1; b.alp[2] = s.al2;
-  b.phase = phase_at(c, tK);
   b.length = p.init_length - st.dl;
   b.width = p.init_width + st.dl;
   b.prev_volume = st.prevV;
@@ -470,6 +417,67 @@ SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDeriv
   b.com_rate = st.s.com_rate;
   b.prev_com_rate = st.prev_com_rate;
   b.com_acc = st.com_acc;
+}
+SALP_HD void mixed_finish_dyn(const Motion32& s, Body64& b) {
+  b.v[0] = s.v0; b.v[1] = s.v1; b.v[2] = s.v2;
+  b.w[0] = s.w0; b.w[1] = s.w1; b.w[2] = s.w2;
+  b.acc[0] = s.ac0; b.acc[1] = s.ac1; b.acc[2] = s.ac2;
+  b.alp[0] = s.al0; b.alp[1] = s.al1; b.alp[2] = s.al2;
+}
+// index of the next shape update after update j (0x7fffffff: none)
+SALP_HD int next_update_after(int j, const PhasePlan& pp) {
+  return (j < pp.upd_a_end || (j >= pp.upd_b_begin && j < pp.upd_b_end)) ? j + 1
+         : (j < pp.upd_b_begin ? pp.upd_b_begin : 0x7fffffff);
+}
+
+template <>
+SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c,
+                                            const double* time_table, Body64& b, double& t_out) {
+  // ---- K: first k with !(t_k < total) in the dtype the reference compares in (robot.py:756) ----
+  const int K = plan_substeps(c, time_table);
+  t_out = 0.0;
+  if (K <= 0) return K;            // K == 0: nothing moves; K < 0: range error (non-finite action)
+  const PhasePlan pp = make_phase_plan(c, time_table, dv.inv_dt);
+  const float dir[3] = {(float)c.dir[0], (float)c.dir[1], (float)c.dir[2]};
+
+  ShapeTrack st;
+  Coef32 g;
+  Motion32 s;
+  mixed_init_shape(p, dv, b, dir, st, g);
+  mixed_init_dyn(b, s);
+  mixed_init_kin(b, s);
+
+  // The kinematic update of substep k-1 only READS the (v, w) that the dynamics of substep k also
+  // only reads, so the loop runs kin(k-1) side by side with dyn(k): two independent dependency
+  // chains per iteration instead of one long one.  Substep 0's dynamics is peeled off in front,
+  // substep K-1's kinematics behind.
+  int next_upd;                     // next update index j at which the shape (or its differences) moves
+  dyn_step(dv, g, s);
+  shape_update(p, dv, c, time_table, dir, 1, pp.k_T0, pp.k_jet, st, g);
+  next_upd = 2;
+
+  int k = 1;
+  while (k < K) {
+    const int kend = k + SALP_MIXED_CHUNK < K ? k + SALP_MIXED_CHUNK : K;
+    for (; k < kend; k++) {
+      kin_step(dv, s);
+      dyn_step(dv, g, s);
+      if (k + 1 == next_upd) {
+        shape_update(p, dv, c, time_table, dir, k + 1, pp.k_T0, pp.k_jet, st, g);
+        next_upd = next_update_after(k + 1, pp);
+      }
+    }
+    flush_chunk(b, s);       // two-level sums (fp32 chunk partials -> fp64 totals)
+  }
+  // ---- the last substep's kinematic update ----
+  kin_step(dv, s);
+  flush_chunk(b, s);
+
+  // ---- epilogue: back to the carried fp64 columns ----
+  const double tK = time_table[K];
+  mixed_finish_dyn(s, b);
+  mixed_finish_shape(p, st, K, b);
+  b.phase = phase_at(c, tK);
   b.speed_world = (double)sqrtf(s.vw0 * s.vw0 + s.vw1 * s.vw1);
   t_out = tK;
   return K;
