@@ -93,7 +93,7 @@ def test_sort_by_k_is_bit_identical():
         env.reset()
         rec = []
         for t in range(T):
-            obs, rew, term, trunc = env.step(acts[t], auto_reset=True, sort_by_k=sort)
+            obs, rew, term, trunc = env.step(acts[t], auto_reset=True, sort_by_k=sort, pipeline=False)
             rec.append((obs.copy(), rew.copy(), term.copy(), trunc.copy(), env.substeps.copy(),
                         env.get_state("posw_x"), env.get_state("euler_z")))
         env.check()
@@ -214,3 +214,36 @@ def test_kernel_cuts_exactly_the_episodes_where_the_reference_raises(precision):
     # these cycles sit next to the integrator's stability limit (transient |v| of 1e3 m/s and more):
     # fp32 rounding is amplified accordingly, hence 1e-3 here instead of the 1e-5 of regular cycles
     assert worst < (1e-9 if precision == PRECISION_F64 else 1e-3), worst
+
+
+def test_pipeline_kernel_matches_fused_kernel():
+    """Small batches run the 3-warp pipeline kernel (salp_pipe_kernel.cuh); it must reproduce the
+    fused kernel: integers and flags exactly, floats to the grouping of the fp32 chunk sums."""
+    n, T = 1000, 12           # not a multiple of 32: ragged last block
+    g = load_golden("ref_random.npz")
+    acts = uniform_actions(np.random.default_rng(12), T, n)
+    acts[0, :8] = [[0, 0, 0], [1, 1, 1], [1, 0, -1], [0.088, 0, 0.5], [0.5, 0.5, 1e-4], [0.09, 0, 0], [0, 1, 1], [1, 1, 0]]
+    pipe = SalpBatch(n, golden_params(g), seed=2)
+    fused = SalpBatch(n, golden_params(g), seed=2)
+    np.testing.assert_array_equal(pipe.reset(), fused.reset())
+    worst = 0.0
+    for t in range(T):
+        o1, r1, te1, tr1 = pipe.step(acts[t], auto_reset=True, pipeline=True)
+        o2, r2, te2, tr2 = fused.step(acts[t], auto_reset=True, pipeline=False)
+        np.testing.assert_array_equal(pipe.substeps, fused.substeps)
+        np.testing.assert_array_equal(te1, te2)
+        np.testing.assert_array_equal(tr1, tr2)
+        for col in ("cycle", "phase", "ep_length", "episode_index"):
+            np.testing.assert_array_equal(pipe.get_state(col), fused.get_state(col))
+        np.testing.assert_allclose(o1, o2, rtol=2e-6, atol=2e-6)
+        np.testing.assert_allclose(r1, r2, rtol=1e-5, atol=2e-4)
+        for col in ("posw_x", "posw_y", "vel_x", "vel_y", "euler_z", "angvel_z", "length", "width", "prev_volume",
+                    "com_x", "com_rate_x", "com_acc_x", "prev_i_y", "pos_x", "angle_z", "acc_x", "angacc_z"):
+            a, b = pipe.get_state(col), fused.get_state(col)
+            ok = np.isfinite(b)
+            np.testing.assert_array_equal(np.isfinite(a), ok)
+            e = np.abs(a[ok] - b[ok]) / np.maximum(np.abs(b[ok]), 0.1)
+            worst = max(worst, float(e.max()))
+            assert e.max() < 2e-6, (col, t, e.max())
+    print("pipeline vs fused: worst relative difference", worst)
+    pipe.check()
