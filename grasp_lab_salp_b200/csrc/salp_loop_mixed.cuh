@@ -243,6 +243,7 @@ struct Motion32 {
   // (sin/cos of roll and pitch are carried: the Euler-rate matrix uses the OLD angles)
   float phi_lo, theta_lo, psi_lo;
   float sph, cph, sth, cth, sps, cps;
+  float rcth;                            // 1 / cos(pitch): Newton-refined from the previous substep's value
   float pw0, pw1, pw2;                   // chunk partial sums: position_world, position, angle
   float pos0, pos1, pos2, ang0, ang1, ang2;
   float vw0, vw1;                        // velocity_world[0:2] of the latest kinematic update
@@ -285,7 +286,7 @@ SALP_HD void rotate_small(float d, float& sn, float& cs) {     // (sin, cos)(x) 
 SALP_HD void kin_step(const SalpDerived& dv, Motion32& s) {
   const float dt = dv.dt;
   const float v0 = s.v0, v1 = s.v1, v2 = s.v2, w0 = s.w0, w1 = s.w1, w2 = s.w2;
-  float rcth = fast_rcp(s.cth);
+  const float rcth = s.rcth;
   float q = s.sph * w1 + s.cph * w2;
   float dphi = fmaf(s.sth * rcth, q, w0) * dt;
   float dtheta = (s.cph * w1 - s.sph * w2) * dt;
@@ -296,6 +297,11 @@ SALP_HD void kin_step(const SalpDerived& dv, Motion32& s) {
   rotate_small(dphi, s.sph, s.cph);
   rotate_small(dtheta, s.sth, s.cth);
   rotate_small(dpsi, s.sps, s.cps);
+  // 1 / cos(pitch) for the next substep: cos(pitch) moved by O(1e-4) relative, so two Newton steps
+  // from the previous reciprocal are exact to fp32 (re-seeded from MUFU.RCP at every flush)
+  float r = s.rcth;
+  r = r * fmaf(-s.cth, r, 2.0f);
+  s.rcth = r * fmaf(-s.cth, r, 2.0f);
   float u1 = s.cph * v1 - s.sph * v2, u2 = s.sph * v1 + s.cph * v2;      // Rx
   float r0 = s.cth * v0 + s.sth * u2, vw2 = s.cth * u2 - s.sth * v0;     // Ry
   s.vw0 = s.cps * r0 - s.sps * u1;                                       // Rz
@@ -305,17 +311,16 @@ SALP_HD void kin_step(const SalpDerived& dv, Motion32& s) {
   s.ang0 = fmaf(w0, dt, s.ang0); s.ang1 = fmaf(w1, dt, s.ang1); s.ang2 = fmaf(w2, dt, s.ang2);
 }
 
-// (sin, cos) of an fp64 angle total, rounded to fp32: the chunk anchor.  Small angles (roll and
-// pitch, nearly always) take the fp32 path; the fp32 rounding of the ARGUMENT is < 6e-8 there.
+// (sin, cos) of an fp64 angle total, rounded to fp32: the chunk anchor.  The fp64 argument is split
+// into hi = (float)x and lo = (float)(x - hi); sincos32(hi) is a 1-ulp fp32 evaluation and lo
+// (<= half an ulp of hi) enters by the first-order angle-addition terms -- no fp64 sincos.
 SALP_HD void anchor_sincos(double x, float& sn, float& cs) {
-  if (fabs(x) < 1.0) {
-    sincos32((float)x, sn, cs);
-  } else {
-    double s64, c64;
-    sincos(x, &s64, &c64);
-    sn = (float)s64;
-    cs = (float)c64;
-  }
+  const float hi = (float)x;
+  const float lo = (float)(x - (double)hi);
+  float s, c;
+  sincos32(hi, s, c);
+  sn = fmaf(c, lo, s);
+  cs = fmaf(-s, lo, c);
 }
 
 // fold the fp32 chunk partials into the fp64 totals and re-anchor the three (sin, cos) pairs
@@ -327,6 +332,7 @@ SALP_HD void flush_chunk(Body64& b, Motion32& s) {
   anchor_sincos(b.eul[0], s.sph, s.cph);
   anchor_sincos(b.eul[1], s.sth, s.cth);
   anchor_sincos(b.eul[2], s.sps, s.cps);
+  s.rcth = fast_rcp(s.cth);
   s.phi_lo = s.theta_lo = s.psi_lo = 0.f;
   s.pw0 = s.pw1 = s.pw2 = 0.f;
   s.pos0 = s.pos1 = s.pos2 = 0.f;
@@ -396,6 +402,7 @@ SALP_HD void mixed_init_kin(const Body64& b, Motion32& s) {
   anchor_sincos(b.eul[0], s.sph, s.cph);
   anchor_sincos(b.eul[1], s.sth, s.cth);
   anchor_sincos(b.eul[2], s.sps, s.cps);
+  s.rcth = fast_rcp(s.cth);
   s.phi_lo = s.theta_lo = s.psi_lo = 0.f;
   s.pw0 = s.pw1 = s.pw2 = 0.f;
   s.pos0 = s.pos1 = s.pos2 = 0.f; s.ang0 = s.ang1 = s.ang2 = 0.f;
