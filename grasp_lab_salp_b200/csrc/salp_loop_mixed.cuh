@@ -185,6 +185,26 @@ SALP_HD void shape64_at(const SalpParams& p, const SalpDerived& k, double lh, do
   I1 = (k.c2 * lh2 + k.c1 * lh + k.c0) + sw * (lh2 + wh2);
   com = (k.comA * lh + k.comB) / (k.mtot0 + wm);
 }
+// The same chain inside the substep loop: the division by the total mass D is replaced by three
+// Newton steps on the reciprocal carried from the previous update (D moves by < 5 % between
+// consecutive updates even next to the integrator's stability limit: (0.05)^8 ~ 4e-11, and
+// ~1e-22 for regular cycles), which takes a ~200-cycle DDIV off the loop's critical path.
+SALP_HD void shape64_step(const SalpParams& p, const SalpDerived& k, double lh, double wh, double& rD, double& V,
+                          double& I0, double& I1, double& com) {
+  double wh2 = wh * wh, lh2 = lh * lh;
+  double Ve = k.four_thirds_pi * lh * wh2;
+  V = Ve - p.tube_volume;
+  double D = k.mtot0 + p.density * V;
+  double sw = k.skin3 + 200.0 * Ve;
+  I0 = sw * (wh2 + wh2);
+  I1 = (k.c2 * lh2 + k.c1 * lh + k.c0) + sw * (lh2 + wh2);
+  double r = rD;
+  r = r * (2.0 - D * r);
+  r = r * (2.0 - D * r);
+  r = r * (2.0 - D * r);
+  rD = r;
+  com = (k.comA * lh + k.comB) * r;
+}
 
 // All fp32 coefficients of the coming substep.  Mass, inertia, areas and drag coefficients are
 // evaluated in fp32 from the half-length / half-width (they are never differenced); the
@@ -343,6 +363,7 @@ SALP_HD void flush_chunk(Body64& b, Motion32& s) {
 struct ShapeTrack {
   Shape64 s;
   double prev_com_rate, com_acc, prevV, I0_prev_used, I1_prev_used, dl;
+  double rD;                    // carried reciprocal of the total mass (shape64_step)
   int last_update;
 };
 
@@ -354,8 +375,8 @@ SALP_HD void shape_update(const SalpParams& p, const SalpDerived& dv, const Cycl
   const int phase = j < k_T0 ? 0 : (j < k_jet ? 1 : 2);
   st.dl = shape_delta(phase, t, c.refill, c.T0, (double)c.contraction32, c.contract_rate, c.release_rate);
   double lh = 0.5 * (p.init_length - st.dl), wh = 0.5 * (p.init_width + st.dl);
-  double V, I0n, I1n, com, wm;
-  shape64_at(p, dv, lh, wh, V, I0n, I1n, com, wm);
+  double V, I0n, I1n, com;
+  shape64_step(p, dv, lh, wh, st.rD, V, I0n, I1n, com);
   double dV_dt = (V - st.s.V) * dv.inv_dt;
   double com_rate = (com - st.s.com) * dv.inv_dt;                // robot.py:901-910
   st.com_acc = (com_rate - st.prev_com_rate) * dv.inv_dt;        // robot.py:912-922
@@ -382,6 +403,7 @@ SALP_HD void mixed_init_shape(const SalpParams& p, const SalpDerived& dv, const 
   st.last_update = 0;
   double lh = 0.5 * b.length, wh = 0.5 * b.width, wm, com_now;
   shape64_at(p, dv, lh, wh, st.s.V, st.s.I0, st.s.I1, com_now, wm);
+  st.rD = 1.0 / (dv.mtot0 + wm);
   double dV_dt = (st.s.V - b.prev_volume) * dv.inv_dt;
   // the carried centre of mass may be stale w.r.t. length/width (Robot.reset quirk, robot.py:478)
   st.s.com = b.com;
@@ -431,6 +453,17 @@ SALP_HD void mixed_finish_dyn(const Motion32& s, Body64& b) {
   b.acc[0] = s.ac0; b.acc[1] = s.ac1; b.acc[2] = s.ac2;
   b.alp[0] = s.al0; b.alp[1] = s.al1; b.alp[2] = s.al2;
 }
+// max over the lanes of the warp that are still in the cycle loop.  The host build (tests/emu)
+// returns "forever": it then runs the shape update after EVERY substep, the most adversarial
+// neighbour a lane can have, so the CPU parity tests cover the no-op property relied on below.
+SALP_HD int warp_max_int(int x) {
+#ifdef __CUDA_ARCH__
+  return __reduce_max_sync(__activemask(), x);
+#else
+  (void)x;
+  return 0x7fffffff;
+#endif
+}
 // index of the next shape update after update j (0x7fffffff: none)
 SALP_HD int next_update_after(int j, const PhasePlan& pp) {
   return (j < pp.upd_a_end || (j >= pp.upd_b_begin && j < pp.upd_b_end)) ? j + 1
@@ -458,23 +491,36 @@ SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDeriv
   // only reads, so the loop runs kin(k-1) side by side with dyn(k): two independent dependency
   // chains per iteration instead of one long one.  Substep 0's dynamics is peeled off in front,
   // substep K-1's kinematics behind.
-  int next_upd;                     // next update index j at which the shape (or its differences) moves
+  //
+  // Shape updates: a lane needs them at j <= upd_a_end and upd_b_begin <= j <= upd_b_end.  Running
+  // the update where the shape is static is a no-op (same shape -> same coefficients, all backward
+  // differences 0), so the loop is split at the warp-uniform end W of the last lane's window:
+  // loop A (j <= W) runs kin, dyn AND the update as one straight-line block -- three independent
+  // chains for the scheduler, no divergent branch --, loop B (the coast, most substeps) runs the
+  // lean body.  With the K-sort's second key (end of shape motion) W is close to every lane's own end.
+  const int lane_end = pp.upd_a_end > pp.upd_b_end ? pp.upd_a_end : pp.upd_b_end;
+  const int W = warp_max_int(lane_end < K ? lane_end : K);
   dyn_step(dv, g, s);
   shape_update(p, dv, c, time_table, dir, 1, pp.k_T0, pp.k_jet, st, g);
-  next_upd = 2;
 
   int k = 1;
+  const int kA = W < K ? W : K;                  // loop A covers updates j = k + 1 <= W
+  while (k < kA) {
+    const int kend = k + SALP_MIXED_CHUNK < kA ? k + SALP_MIXED_CHUNK : kA;
+    for (; k < kend; k++) {
+      kin_step(dv, s);
+      dyn_step(dv, g, s);
+      shape_update(p, dv, c, time_table, dir, k + 1, pp.k_T0, pp.k_jet, st, g);
+    }
+    flush_chunk(b, s);       // two-level sums (fp32 chunk partials -> fp64 totals)
+  }
   while (k < K) {
     const int kend = k + SALP_MIXED_CHUNK < K ? k + SALP_MIXED_CHUNK : K;
     for (; k < kend; k++) {
       kin_step(dv, s);
       dyn_step(dv, g, s);
-      if (k + 1 == next_upd) {
-        shape_update(p, dv, c, time_table, dir, k + 1, pp.k_T0, pp.k_jet, st, g);
-        next_upd = next_update_after(k + 1, pp);
-      }
     }
-    flush_chunk(b, s);       // two-level sums (fp32 chunk partials -> fp64 totals)
+    flush_chunk(b, s);
   }
   // ---- the last substep's kinematic update ----
   kin_step(dv, s);
