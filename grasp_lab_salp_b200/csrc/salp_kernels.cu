@@ -111,8 +111,9 @@ int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& i
     order = scratch.order;
   }
   const int block = block_for(v.n);
-  // small batches that fit one wave of 32-env blocks: the warp-specialised pipeline
-  if (p.precision == SALP_PRECISION_MIXED && !order && !(flags & SALP_STEP_NO_PIPELINE) &&
+  // opt-in for small batches that fit one wave of 32-env blocks: the warp-specialised pipeline
+  // (experimental: the fused latency kernel is currently faster, see profiles/README.md)
+  if (p.precision == SALP_PRECISION_MIXED && !order && (flags & SALP_STEP_PIPELINE) &&
       v.n <= (int64_t)32 * (v.sm_count > 0 ? v.sm_count : 148)) {
     static bool configured = false;
     if (!configured) {

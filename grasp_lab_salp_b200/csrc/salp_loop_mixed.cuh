@@ -189,8 +189,8 @@ SALP_HD void shape64_at(const SalpParams& p, const SalpDerived& k, double lh, do
 // Newton steps on the reciprocal carried from the previous update (D moves by < 5 % between
 // consecutive updates even next to the integrator's stability limit: (0.05)^8 ~ 4e-11, and
 // ~1e-22 for regular cycles), which takes a ~200-cycle DDIV off the loop's critical path.
-SALP_HD void shape64_step(const SalpParams& p, const SalpDerived& k, double lh, double wh, double& rD, double& V,
-                          double& I0, double& I1, double& com) {
+SALP_HD void shape64_step(const SalpParams& p, const SalpDerived& k, double lh, double wh, double& rD, double& Dprev,
+                          double& V, double& I0, double& I1, double& com) {
   double wh2 = wh * wh, lh2 = lh * lh;
   double Ve = k.four_thirds_pi * lh * wh2;
   V = Ve - p.tube_volume;
@@ -202,7 +202,9 @@ SALP_HD void shape64_step(const SalpParams& p, const SalpDerived& k, double lh, 
   r = r * (2.0 - D * r);
   r = r * (2.0 - D * r);
   r = r * (2.0 - D * r);
+  r = (D == Dprev) ? rD : r;      // unchanged shape: keep the reciprocal bit for bit (the update is then an exact no-op)
   rD = r;
+  Dprev = D;
   com = (k.comA * lh + k.comB) * r;
 }
 
@@ -363,7 +365,7 @@ SALP_HD void flush_chunk(Body64& b, Motion32& s) {
 struct ShapeTrack {
   Shape64 s;
   double prev_com_rate, com_acc, prevV, I0_prev_used, I1_prev_used, dl;
-  double rD;                    // carried reciprocal of the total mass (shape64_step)
+  double rD, Dprev;             // carried reciprocal of the total mass and the mass it belongs to (shape64_step)
   int last_update;
 };
 
@@ -376,7 +378,7 @@ SALP_HD void shape_update(const SalpParams& p, const SalpDerived& dv, const Cycl
   st.dl = shape_delta(phase, t, c.refill, c.T0, (double)c.contraction32, c.contract_rate, c.release_rate);
   double lh = 0.5 * (p.init_length - st.dl), wh = 0.5 * (p.init_width + st.dl);
   double V, I0n, I1n, com;
-  shape64_step(p, dv, lh, wh, st.rD, V, I0n, I1n, com);
+  shape64_step(p, dv, lh, wh, st.rD, st.Dprev, V, I0n, I1n, com);
   double dV_dt = (V - st.s.V) * dv.inv_dt;
   double com_rate = (com - st.s.com) * dv.inv_dt;                // robot.py:901-910
   st.com_acc = (com_rate - st.prev_com_rate) * dv.inv_dt;        // robot.py:912-922
@@ -403,7 +405,8 @@ SALP_HD void mixed_init_shape(const SalpParams& p, const SalpDerived& dv, const 
   st.last_update = 0;
   double lh = 0.5 * b.length, wh = 0.5 * b.width, wm, com_now;
   shape64_at(p, dv, lh, wh, st.s.V, st.s.I0, st.s.I1, com_now, wm);
-  st.rD = 1.0 / (dv.mtot0 + wm);
+  st.Dprev = dv.mtot0 + wm;
+  st.rD = 1.0 / st.Dprev;
   double dV_dt = (st.s.V - b.prev_volume) * dv.inv_dt;
   // the carried centre of mass may be stale w.r.t. length/width (Robot.reset quirk, robot.py:478)
   st.s.com = b.com;

@@ -21,7 +21,7 @@ PRECISION_MIXED = 1
 
 STEP_AUTORESET = 1
 STEP_SORT_BY_K = 2
-STEP_NO_PIPELINE = 4
+STEP_PIPELINE = 4
 
 REWARD_TERM_NAMES = ("rewards/track", "rewards/heading", "rewards/smooth", "rewards/yaw",
                      "rewards/time", "rewards/sideslip", "rewards/obstacle")

@@ -57,7 +57,7 @@ typedef enum SalpPrecision {
 /* salp_step flags */
 #define SALP_STEP_AUTORESET 1u     /* SB3 VecEnv semantics: reset finished envs, obs = post-reset obs */
 #define SALP_STEP_SORT_BY_K 2u     /* balance warps: order envs by substep count before the loop */
-#define SALP_STEP_NO_PIPELINE 4u   /* small batches: use the fused latency kernel instead of the 3-warp pipeline */
+#define SALP_STEP_PIPELINE 4u      /* small batches (<= 32 envs per SM): run the 3-warp shape->dyn->kin pipeline kernel */
 
 /*
  * Every literal the reference hard-codes on this path, as one POD.
