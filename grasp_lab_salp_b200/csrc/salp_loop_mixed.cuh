@@ -462,6 +462,8 @@ SALP_HD void mixed_finish_dyn(const Motion32& s, Body64& b) {
 SALP_HD int warp_max_int(int x) {
 #ifdef __CUDA_ARCH__
   return __reduce_max_sync(__activemask(), x);
+#elif defined(SALP_EMU_LANE_ONLY)
+  return x;
 #else
   (void)x;
   return 0x7fffffff;
@@ -507,23 +509,24 @@ SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDeriv
   shape_update(p, dv, c, time_table, dir, 1, pp.k_T0, pp.k_jet, st, g);
 
   int k = 1;
-  const int kA = W < K ? W : K;                  // loop A covers updates j = k + 1 <= W
-  while (k < kA) {
-    const int kend = k + SALP_MIXED_CHUNK < kA ? k + SALP_MIXED_CHUNK : kA;
-    for (; k < kend; k++) {
+  const int kA = W < K ? W : K;                  // part A covers updates j = k + 1 <= W
+  // Chunk boundaries are FIXED (after iterations 16, 32, ...: kinematic updates 0..15, 16..31, ...)
+  // so that the grouping of the fp32 chunk sums -- hence every bit of the result -- does not
+  // depend on W, i.e. on which envs share the warp.
+  while (k < K) {
+    const int boundary = ((k - 1) & ~(SALP_MIXED_CHUNK - 1)) + SALP_MIXED_CHUNK + 1;
+    const int cend = boundary < K ? boundary : K;
+    const int aend = kA < cend ? kA : cend;
+    for (; k < aend; k++) {
       kin_step(dv, s);
       dyn_step(dv, g, s);
       shape_update(p, dv, c, time_table, dir, k + 1, pp.k_T0, pp.k_jet, st, g);
     }
-    flush_chunk(b, s);       // two-level sums (fp32 chunk partials -> fp64 totals)
-  }
-  while (k < K) {
-    const int kend = k + SALP_MIXED_CHUNK < K ? k + SALP_MIXED_CHUNK : K;
-    for (; k < kend; k++) {
+    for (; k < cend; k++) {
       kin_step(dv, s);
       dyn_step(dv, g, s);
     }
-    flush_chunk(b, s);
+    if (k == boundary) flush_chunk(b, s);       // two-level sums (fp32 chunk partials -> fp64 totals)
   }
   // ---- the last substep's kinematic update ----
   kin_step(dv, s);

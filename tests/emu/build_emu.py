@@ -23,19 +23,23 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build() -> str:
+def build(lane_only: bool = False) -> str:
+    """lane_only=False: the shape update runs after EVERY substep (the most adversarial warp
+    neighbour); lane_only=True: only inside the env's own update windows (a warp of one)."""
     os.makedirs(OUT, exist_ok=True)
-    stamp = os.path.join(OUT, "emu.hash")
+    lib = os.path.join(OUT, "libsalp_emu_lane.so") if lane_only else LIB
+    stamp = lib + ".hash"
     d = _digest()
-    if os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == d:
-        return LIB
+    if os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == d:
+        return lib
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     # host code is what runs; the (unused) device pass still needs an arch.  No contraction on the
     # host so that fp32/fp64 products and sums round separately, like the oracle build.
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-shared",
-           "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-mfma", "-o", LIB,
+           *(["-DSALP_EMU_LANE_ONLY"] if lane_only else []),
+           "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-mfma", "-o", lib,
            os.path.join(HERE, "salp_emu.cu")]
     subprocess.run(cmd, check=True, capture_output=True, text=True)
     with open(stamp, "w") as f:
         f.write(d)
-    return LIB
+    return lib

@@ -25,3 +25,13 @@ def emu_cdll():
 
 def EmuBatch(num_envs, params=None, **kw):
     return SalpBatch(num_envs, params, _cdll=emu_cdll(), **kw)
+
+
+_cdll_lane = None
+
+
+def emu_lane_cdll():
+    global _cdll_lane
+    if _cdll_lane is None:
+        _cdll_lane = _lib.bind(C.CDLL(build_emu.build(lane_only=True)), names=_EMU_SYMBOLS)
+    return _cdll_lane

@@ -3,7 +3,7 @@ the live Python reference and against the C oracle.  Checks kernel LOGIC without
 import numpy as np
 import pytest
 
-from emu_backend import EmuBatch
+from emu_backend import EmuBatch, emu_cdll, emu_lane_cdll
 from grasp_lab_salp_b200 import PRECISION_F64, PRECISION_MIXED
 from oracle.salp_oracle import OracleVecEnv
 from parity import check_blowup_golden, TOL_F64, TOL_MIXED, TOL_MIXED_FREE_RUN, golden_params, lockstep_compare, sample_scene_pool, load_golden, replay_golden
@@ -74,3 +74,28 @@ def test_emu_f64_lockstep_vs_oracle_with_autoreset():
 def test_emu_cuts_exactly_the_episodes_where_the_reference_raises(precision):
     worst = check_blowup_golden(lambda n, g: EmuBatch(n, golden_params(g, precision=precision)))
     assert worst < (1e-9 if precision == PRECISION_F64 else 1e-5), worst
+
+
+def test_redundant_shape_updates_are_exact_noops():
+    """The fused loop runs the shape update up to the warp-uniform end of the LAST lane's window, so
+    a lane may see updates it does not need.  They must not change a single bit: the host build
+    that updates after every substep equals the one that updates only inside the env's own
+    windows, column for column (this is what makes results independent of warp composition,
+    hence of sorting and sharding)."""
+    from grasp_lab_salp_b200.batch import SalpBatch
+    from grasp_lab_salp_b200.params import FIELDS
+    n = 400
+    a = SalpBatch(n, seed=3, _cdll=emu_cdll())
+    b = SalpBatch(n, seed=3, _cdll=emu_lane_cdll())
+    a.reset()
+    b.reset()
+    rng = np.random.default_rng(0)
+    for t in range(5):
+        act = rng.uniform([0, 0, -1], [1, 1, 1], size=(n, 3)).astype(np.float32)
+        if t == 2:
+            act = np.clip(rng.normal(size=(n, 3)), [0, 0, -1], [1, 1, 1]).astype(np.float32)
+        a.step(act, auto_reset=True)
+        b.step(act, auto_reset=True)
+        for col in FIELDS:
+            x, y = a.get_state(col), b.get_state(col)
+            assert np.array_equal(x, y, equal_nan=True), (t, col)
