@@ -404,7 +404,7 @@ def run_cuda_arm(args):
                        "(256 MiB memset outside the per-step event pairs)", "parallelism": f"env-shard x{world}"},
             "substeps_per_sec": sub_rate, "mean_substeps_per_env_step": total_substeps / total_env_steps,
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak, "traffic": None,
+                         "frac": achieved_tf / peak, "traffic": ncu_traffic(n, args.precision),
                          "peak_source": ("measured in this run: salp_probe_fp32_peak (FFMA, 2048 thr/SM)"
                                          if fp32_peak else "nominal"),
                          "nominal_peak": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved_tf / NOMINAL_FP32_TFLOPS,
@@ -423,6 +423,16 @@ def run_cuda_arm(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(envs, precision):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE step-kernel launch from the committed
+    `ncu --set full` capture of this workload (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(f"{precision}:{envs}")
+    except Exception:
+        return None
 
 
 def state_bytes_per_env_step(params):
