@@ -20,7 +20,7 @@ salp_step_kernel_lat(const __grid_constant__ SalpParams p, const __grid_constant
 }
 
 template <int PREC>
-__global__ void __launch_bounds__(128, 5)
+__global__ void __launch_bounds__(128, 4)
 salp_step_kernel(const __grid_constant__ SalpParams p, const __grid_constant__ SalpDerived dv,
                  const __grid_constant__ SalpView v, const __grid_constant__ SalpStepIO io, uint32_t flags,
                  const int32_t* __restrict__ order) {
