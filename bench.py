@@ -268,6 +268,7 @@ def run_cuda_arm(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
