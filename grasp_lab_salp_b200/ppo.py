@@ -1,0 +1,326 @@
+"""PPO on device tensors over the batched SALP simulator.
+
+Stands in for stable-baselines3 ``PPO("MlpPolicy", vec_env)`` with SB3's defaults (the reference
+ships SAC and RecurrentPPO scripts only -- src/train_robot.py:62-69, src/train_robot_recurrent_ppo.py
+:85-107 -- and BASELINE.json config 3 asks for "PPO MLP policy ... with 16k envs", so SB3's PPO
+defaults are the stand-in):
+
+  * policy: separate actor / critic MLPs 64-64 tanh, orthogonal init (gain sqrt(2); 0.01 on the
+    action head, 1 on the value head), state-independent log_std = 0, diagonal Gaussian;
+    actions are clipped to the Box only when handed to the env (SB3 on-policy collect_rollouts);
+  * GAE(gamma = 0.99, lambda = 0.95); on a TimeLimit truncation the reward is bootstrapped with
+    gamma * V(terminal_observation), as SB3 does;
+  * clipped surrogate (0.2), value coefficient 0.5, entropy coefficient 0, advantage
+    normalisation per minibatch, Adam 3e-4, gradient clipping at 0.5, 10 epochs per rollout.
+
+Nothing leaves the GPU: the rollout buffer, the policy forward (cuBLAS GEMMs -- the only dense
+algebra here) and ``SalpBatch.step_device`` all work on device tensors; per-iteration statistics
+are reduced on device and read back once.  Multi-GPU: one process per GPU, envs sharded
+(``distributed.make_shard``), gradients and rollout statistics all-reduced over NCCL.
+
+The env is anything with ``num_envs``, ``obs_dim``, ``reset_t() -> obs`` and
+``step_t(actions) -> (obs, reward, terminated, truncated, terminal_obs)`` on torch tensors;
+``DeviceEnv`` adapts a SalpBatch (CUDA), ``HostEnv`` adapts any numpy backend with the SalpBatch
+host face (the CPU oracle and the host build of the kernel body in the tests).
+"""
+from __future__ import annotations
+
+import math
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+
+# ------------------------------------------------------------------------------------------------
+# env adapters
+# ------------------------------------------------------------------------------------------------
+class DeviceEnv:
+    """SalpBatch device face: zero-copy, asynchronous on the current stream."""
+
+    def __init__(self, batch, sort_by_k="auto"):
+        self.batch = batch
+        self.num_envs, self.obs_dim = batch.num_envs, batch.obs_dim
+        self.device = torch.device("cuda", batch.device)
+        self.sort = batch.num_envs >= 32768 if sort_by_k == "auto" else bool(sort_by_k)
+
+    def reset_t(self):
+        return self.batch.reset_device().clone()
+
+    def step_t(self, actions):
+        obs, rew, term, trunc = self.batch.step_device(actions, auto_reset=True, sort_by_k=self.sort)
+        return obs, rew, term.bool(), trunc.bool(), self.batch.dev["terminal_obs"]
+
+
+class HostEnv:
+    """Any backend with the numpy face of SalpBatch (oracle, host build of the kernel body)."""
+
+    def __init__(self, backend, device="cpu"):
+        self.b = backend
+        self.num_envs, self.obs_dim = backend.num_envs, backend.obs_dim
+        self.device = torch.device(device)
+
+    def reset_t(self):
+        return torch.from_numpy(self.b.reset().copy()).to(self.device)
+
+    def step_t(self, actions):
+        obs, rew, term, trunc = self.b.step(actions.detach().cpu().numpy().astype(np.float32), auto_reset=True)
+        t = lambda a, dt=None: torch.from_numpy(np.array(a, dtype=dt)).to(self.device)  # noqa: E731
+        return (t(obs, np.float32), t(rew, np.float32), t(term, bool), t(trunc, bool),
+                t(self.b.terminal_obs, np.float32))
+
+
+# ------------------------------------------------------------------------------------------------
+# policy (SB3 MlpPolicy defaults)
+# ------------------------------------------------------------------------------------------------
+def _mlp(inp, hidden, out, out_gain):
+    layers, d = [], inp
+    for h in hidden:
+        lin = nn.Linear(d, h)
+        nn.init.orthogonal_(lin.weight, gain=math.sqrt(2))
+        nn.init.zeros_(lin.bias)
+        layers += [lin, nn.Tanh()]
+        d = h
+    head = nn.Linear(d, out)
+    nn.init.orthogonal_(head.weight, gain=out_gain)
+    nn.init.zeros_(head.bias)
+    return nn.Sequential(*layers, head)
+
+
+class MlpPolicy(nn.Module):
+    def __init__(self, obs_dim=10, act_dim=3, hidden=(64, 64), log_std_init=0.0):
+        super().__init__()
+        self.actor = _mlp(obs_dim, hidden, act_dim, 0.01)
+        self.critic = _mlp(obs_dim, hidden, 1, 1.0)
+        self.log_std = nn.Parameter(torch.full((act_dim,), float(log_std_init)))
+
+    def dist(self, obs):
+        return torch.distributions.Normal(self.actor(obs), self.log_std.exp())
+
+    def value(self, obs):
+        return self.critic(obs).squeeze(-1)
+
+    @torch.no_grad()
+    def act(self, obs, generator=None):
+        mean = self.actor(obs)
+        noise = torch.randn(mean.shape, device=mean.device, dtype=mean.dtype, generator=generator)
+        a = mean + noise * self.log_std.exp()
+        logp = (-0.5 * noise.pow(2) - self.log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
+        return a, logp, self.value(obs)
+
+    def evaluate(self, obs, actions):
+        d = self.dist(obs)
+        return d.log_prob(actions).sum(-1), d.entropy().sum(-1), self.value(obs)
+
+
+# ------------------------------------------------------------------------------------------------
+# PPO
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class PPOConfig:
+    n_steps: int = 32                 # rollout length per env (SB3 default 2048 is for 1 env)
+    n_epochs: int = 10
+    batch_size: int = 16384           # minibatch (SB3 default 64 is for 2048-sample rollouts)
+    gamma: float = 0.99
+    gae_lambda: float = 0.95
+    clip_range: float = 0.2
+    vf_coef: float = 0.5
+    ent_coef: float = 0.0
+    max_grad_norm: float = 0.5
+    learning_rate: float = 3e-4
+    normalize_advantage: bool = True
+    seed: int = 0
+    hidden: tuple = (64, 64)
+    action_low: tuple = (0.0, 0.0, -1.0)     # the Box of salp_robot_env.py:63-67
+    action_high: tuple = (1.0, 1.0, 1.0)
+
+
+def compute_gae(rewards, values, dones, last_value, gamma, lam):
+    """rewards/values/dones: [T, N]; dones[t] = episode ended AT step t (so step t+1 starts a new
+    episode).  Returns (advantages, returns), SB3 RolloutBuffer.compute_returns_and_advantage."""
+    T = rewards.shape[0]
+    adv = torch.zeros_like(rewards)
+    last = torch.zeros_like(last_value)
+    for t in reversed(range(T)):
+        next_value = last_value if t == T - 1 else values[t + 1]
+        nonterminal = (~dones[t]).to(rewards.dtype)
+        delta = rewards[t] + gamma * next_value * nonterminal - values[t]
+        last = delta + gamma * lam * nonterminal * last
+        adv[t] = last
+    return adv, adv + values
+
+
+@dataclass
+class PPOStats:
+    iteration: int = 0
+    env_steps: int = 0
+    mean_step_reward: float = 0.0
+    episodes: int = 0
+    mean_episode_return: float = float("nan")
+    mean_episode_length: float = float("nan")
+    success_rate: float = float("nan")
+    approx_kl: float = 0.0
+    clip_fraction: float = 0.0
+    value_loss: float = 0.0
+    policy_loss: float = 0.0
+    rollout_seconds: float = 0.0
+    update_seconds: float = 0.0
+    history: list = field(default_factory=list, repr=False)
+
+
+class PPO:
+    def __init__(self, env, config: PPOConfig | None = None, policy: MlpPolicy | None = None):
+        self.env = env
+        self.cfg = config or PPOConfig()
+        self.device = env.device
+        torch.manual_seed(self.cfg.seed)
+        self.policy = (policy or MlpPolicy(env.obs_dim, 3, self.cfg.hidden)).to(self.device)
+        self.opt = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.learning_rate, eps=1e-5)
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(self.cfg.seed + 1)
+        self.low = torch.tensor(self.cfg.action_low, device=self.device)
+        self.high = torch.tensor(self.cfg.action_high, device=self.device)
+        self.obs = env.reset_t()
+        n = env.num_envs
+        self._ep_ret = torch.zeros(n, device=self.device)
+        self._ep_len = torch.zeros(n, device=self.device)
+        self.env_steps = 0
+        self.iteration = 0
+        self.dist_world = 1
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.dist_world = dist.get_world_size()
+                for p in self.policy.parameters():          # identical initial weights on every rank
+                    dist.broadcast(p.data, src=0)
+        except Exception:
+            pass
+
+    # ---- rollout ----
+    def collect(self):
+        cfg, env, T, N = self.cfg, self.env, self.cfg.n_steps, self.env.num_envs
+        dev = self.device
+        obs_buf = torch.empty((T, N, env.obs_dim), device=dev)
+        act_buf = torch.empty((T, N, 3), device=dev)
+        logp_buf = torch.empty((T, N), device=dev)
+        val_buf = torch.empty((T, N), device=dev)
+        rew_buf = torch.empty((T, N), device=dev)
+        done_buf = torch.empty((T, N), dtype=torch.bool, device=dev)
+        # episode statistics as masked device-side sums: no host synchronisation inside the rollout
+        ep = torch.zeros(4, dtype=torch.float64, device=dev)       # [sum return, sum length, successes, episodes]
+        for t in range(T):
+            a, logp, v = self.policy.act(self.obs, self.gen)
+            obs_buf[t], act_buf[t], logp_buf[t], val_buf[t] = self.obs, a, logp, v
+            clipped = torch.minimum(torch.maximum(a, self.low), self.high).float().contiguous()
+            obs, rew, term, trunc, term_obs = env.step_t(clipped)
+            done = term | trunc
+            timeout = (trunc & ~term).float()
+            with torch.no_grad():                 # SB3: bootstrap truncated episodes with V(terminal_observation)
+                rew = rew + cfg.gamma * self.policy.value(term_obs) * timeout
+            rew = torch.nan_to_num(rew, nan=0.0, posinf=0.0, neginf=0.0)
+            rew_buf[t], done_buf[t] = rew, done
+            self._ep_ret += rew
+            self._ep_len += 1
+            d = done.to(torch.float64)
+            ep += torch.stack([(self._ep_ret.double() * d).sum(), (self._ep_len.double() * d).sum(),
+                               (term.double() * d).sum(), d.sum()])
+            keep = (~done).float()
+            self._ep_ret *= keep
+            self._ep_len *= keep
+            self.obs = obs.clone()
+        with torch.no_grad():
+            last_value = self.policy.value(self.obs)
+        adv, ret = compute_gae(rew_buf, val_buf, done_buf, last_value, cfg.gamma, cfg.gae_lambda)
+        self.env_steps += T * N
+        episodes = ep
+        flat = lambda x: x.reshape(T * N, *x.shape[2:])  # noqa: E731
+        return dict(obs=flat(obs_buf), act=flat(act_buf), logp=flat(logp_buf), val=flat(val_buf), adv=flat(adv),
+                    ret=flat(ret), mean_reward=rew_buf.mean(), episodes=episodes)
+
+    # ---- update ----
+    def _allreduce_grads(self):
+        if self.dist_world == 1:
+            return
+        import torch.distributed as dist
+        grads = [p.grad for p in self.policy.parameters() if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat)                     # ONE bucket: ~40 KB for the 64-64 MLP (latency-bound)
+        flat /= self.dist_world
+        off = 0
+        for g in grads:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+
+    def update(self, roll):
+        cfg = self.cfg
+        n = roll["obs"].shape[0]
+        bs = min(cfg.batch_size, n)
+        kl = clipf = vl = pl = 0.0
+        count = 0
+        for _ in range(cfg.n_epochs):
+            perm = torch.randperm(n, device=self.device, generator=self.gen)
+            for s in range(0, n - bs + 1, bs):
+                idx = perm[s:s + bs]
+                adv = roll["adv"][idx]
+                if cfg.normalize_advantage:
+                    adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+                logp, ent, val = self.policy.evaluate(roll["obs"][idx], roll["act"][idx])
+                ratio = (logp - roll["logp"][idx]).exp()
+                p1, p2 = adv * ratio, adv * ratio.clamp(1 - cfg.clip_range, 1 + cfg.clip_range)
+                policy_loss = -torch.minimum(p1, p2).mean()
+                value_loss = (roll["ret"][idx] - val).pow(2).mean()
+                loss = policy_loss + cfg.vf_coef * value_loss - cfg.ent_coef * ent.mean()
+                self.opt.zero_grad(set_to_none=True)
+                loss.backward()
+                self._allreduce_grads()
+                nn.utils.clip_grad_norm_(self.policy.parameters(), cfg.max_grad_norm)
+                self.opt.step()
+                with torch.no_grad():
+                    lr = logp - roll["logp"][idx]
+                    kl += float(((lr.exp() - 1) - lr).mean())
+                    clipf += float(((ratio - 1).abs() > cfg.clip_range).float().mean())
+                    vl += float(value_loss)
+                    pl += float(policy_loss)
+                count += 1
+        c = max(count, 1)
+        return dict(approx_kl=kl / c, clip_fraction=clipf / c, value_loss=vl / c, policy_loss=pl / c)
+
+    def _reduce_stat(self, total, count):
+        if self.dist_world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([total, count], dtype=torch.float64, device=self.device)
+            dist.all_reduce(t)                    # rollout statistics: 16 bytes
+            total, count = float(t[0]), float(t[1])
+        return total / count if count else float("nan"), int(count)
+
+    def learn(self, total_env_steps: int, log=None) -> PPOStats:
+        stats = PPOStats()
+        per_iter = self.cfg.n_steps * self.env.num_envs * self.dist_world
+        while self.env_steps * self.dist_world < total_env_steps:
+            t0 = time.perf_counter()
+            roll = self.collect()
+            if self.device.type == "cuda":
+                torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            upd = self.update(roll)
+            if self.device.type == "cuda":
+                torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            self.iteration += 1
+            ep = roll["episodes"].tolist()            # one read-back per iteration
+            ne = int(ep[3])
+            mean_ret, n_ep = self._reduce_stat(ep[0], ne)
+            mean_len, _ = self._reduce_stat(ep[1], ne)
+            succ, _ = self._reduce_stat(ep[2], ne)
+            mean_rew, _ = self._reduce_stat(float(roll["mean_reward"]), 1)
+            row = dict(iteration=self.iteration, env_steps=self.iteration * per_iter, mean_step_reward=mean_rew,
+                       episodes=n_ep, mean_episode_return=mean_ret, mean_episode_length=mean_len, success_rate=succ,
+                       rollout_seconds=t1 - t0, update_seconds=t2 - t1, **upd)
+            stats.history.append(row)
+            for k, v in row.items():
+                setattr(stats, k, v)
+            if log:
+                log(row)
+        return stats

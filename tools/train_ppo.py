@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Train PPO (MLP policy, SB3 defaults) on the batched GPU simulator -- BASELINE config 3.
+
+    python tools/train_ppo.py --envs 16384 --total-steps 10000000 --out gpurun_out/ppo_curve.jsonl
+    torchrun --nproc-per-node 8 tools/train_ppo.py --envs 65536 ...      (envs = whole job, sharded)
+
+Writes one JSON line per PPO iteration (env_steps, mean step reward, mean episode return /
+length, success rate, approx KL, wall seconds for rollout and update).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from grasp_lab_salp_b200 import PRECISION_F64, PRECISION_MIXED, default_params  # noqa: E402
+from grasp_lab_salp_b200.distributed import make_shard, world_info  # noqa: E402
+from grasp_lab_salp_b200.ppo import PPO, DeviceEnv, PPOConfig  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=16384)
+    ap.add_argument("--total-steps", type=int, default=10_000_000)
+    ap.add_argument("--n-steps", type=int, default=32)
+    ap.add_argument("--n-epochs", type=int, default=10)
+    ap.add_argument("--batch-size", type=int, default=16384)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--precision", choices=["mixed", "f64"], default="mixed")
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    rank, local, world = world_info()
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    params = default_params(precision=PRECISION_MIXED if args.precision == "mixed" else PRECISION_F64)
+    batch = make_shard(args.envs, params, seed=args.seed)
+    ppo = PPO(DeviceEnv(batch), PPOConfig(n_steps=args.n_steps, n_epochs=args.n_epochs, batch_size=args.batch_size,
+                                          seed=args.seed))
+    out = open(args.out, "w") if (args.out and rank == 0) else None
+    t0 = time.perf_counter()
+
+    def log(row):
+        if rank == 0:
+            row = dict(row, wall_seconds=time.perf_counter() - t0)
+            line = json.dumps(row)
+            print(line, flush=True)
+            if out:
+                out.write(line + "\n")
+                out.flush()
+
+    stats = ppo.learn(args.total_steps, log=log)
+    batch.check()
+    if rank == 0:
+        wall = time.perf_counter() - t0
+        sim = sum(h["rollout_seconds"] for h in stats.history)
+        print(json.dumps({"summary": True, "envs": args.envs, "gpus": world, "env_steps": stats.env_steps,
+                          "wall_seconds": wall, "env_steps_per_sec_incl_learner": stats.env_steps / wall,
+                          "env_steps_per_sec_rollout_only": stats.env_steps / sim,
+                          "final_success_rate": stats.success_rate,
+                          "final_mean_episode_return": stats.mean_episode_return}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
