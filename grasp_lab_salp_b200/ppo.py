@@ -131,6 +131,10 @@ class PPOConfig:
     max_grad_norm: float = 0.5
     learning_rate: float = 3e-4
     normalize_advantage: bool = True
+    reward_clip: float = 1000.0       # |r| cap for the learner only (legitimate rewards are within [-500, 500]); the
+                                      # reference env returns finite but astronomically large rewards for cycles next
+                                      # to its integrator's stability limit, which would destroy any
+                                      # value function; set to 0 to disable
     seed: int = 0
     hidden: tuple = (64, 64)
     action_low: tuple = (0.0, 0.0, -1.0)     # the Box of salp_robot_env.py:63-67
@@ -220,6 +224,8 @@ class PPO:
             with torch.no_grad():                 # SB3: bootstrap truncated episodes with V(terminal_observation)
                 rew = rew + cfg.gamma * self.policy.value(term_obs) * timeout
             rew = torch.nan_to_num(rew, nan=0.0, posinf=0.0, neginf=0.0)
+            if cfg.reward_clip > 0:
+                rew = rew.clamp(-cfg.reward_clip, cfg.reward_clip)
             rew_buf[t], done_buf[t] = rew, done
             self._ep_ret += rew
             self._ep_len += 1
