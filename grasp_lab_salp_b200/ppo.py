@@ -330,3 +330,140 @@ class PPO:
             if log:
                 log(row)
         return stats
+
+
+# ------------------------------------------------------------------------------------------------
+# RecurrentPPO (sb3_contrib MlpLstmPolicy as configured by src/train_robot_recurrent_ppo.py:85-107)
+# ------------------------------------------------------------------------------------------------
+class LstmPolicy(nn.Module):
+    """lstm_hidden_size = 256, n_lstm_layers = 1, shared_lstm = False, enable_critic_lstm = True
+    (train_robot_recurrent_ppo.py:100-105): separate actor / critic LSTMs on the flattened
+    observation, each followed by the default 64-64 tanh MLP and a linear head."""
+
+    def __init__(self, obs_dim=10, act_dim=3, lstm_hidden=256, hidden=(64, 64), log_std_init=0.0):
+        super().__init__()
+        self.lstm_hidden = lstm_hidden
+        self.lstm_actor = nn.LSTMCell(obs_dim, lstm_hidden)
+        self.lstm_critic = nn.LSTMCell(obs_dim, lstm_hidden)
+        self.actor = _mlp(lstm_hidden, hidden, act_dim, 0.01)
+        self.critic = _mlp(lstm_hidden, hidden, 1, 1.0)
+        self.log_std = nn.Parameter(torch.full((act_dim,), float(log_std_init)))
+
+    def initial_state(self, n, device):
+        z = lambda: torch.zeros(n, self.lstm_hidden, device=device)  # noqa: E731
+        return (z(), z(), z(), z())
+
+    def step(self, obs, state, starts):
+        """One time step.  starts [N] (bool / 0-1): the env began a new episode at this step, so
+        its hidden state is reset first (sb3_contrib _process_sequence)."""
+        keep = (1.0 - starts.float()).unsqueeze(-1)
+        ha, ca, hc, cc = state
+        ha, ca = self.lstm_actor(obs, (ha * keep, ca * keep))
+        hc, cc = self.lstm_critic(obs, (hc * keep, cc * keep))
+        return self.actor(ha), self.critic(hc).squeeze(-1), (ha, ca, hc, cc)
+
+    def peek_value(self, obs, state):
+        hc, _ = self.lstm_critic(obs, (state[2], state[3]))
+        return self.critic(hc).squeeze(-1)
+
+
+class RecurrentPPO(PPO):
+    """PPO with the LSTM policy.  Rollouts carry the per-env LSTM state (reset on done); the
+    update replays whole [T, envs] sequences from the stored initial state, so back-propagation
+    through time spans the rollout (n_steps) with resets at episode starts.  Minibatches are
+    subsets of envs (`batch_size` samples = batch_size // n_steps env sequences)."""
+
+    def __init__(self, env, config: PPOConfig | None = None, policy: LstmPolicy | None = None):
+        cfg = config or PPOConfig(n_steps=32, batch_size=32 * 512)
+        super().__init__(env, cfg, policy or LstmPolicy(env.obs_dim, 3, hidden=cfg.hidden))
+        self.state = self.policy.initial_state(env.num_envs, self.device)
+        self.starts = torch.ones(env.num_envs, dtype=torch.bool, device=self.device)
+
+    def collect(self):
+        cfg, env, T, N = self.cfg, self.env, self.cfg.n_steps, self.env.num_envs
+        dev = self.device
+        obs_buf = torch.empty((T, N, env.obs_dim), device=dev)
+        act_buf = torch.empty((T, N, 3), device=dev)
+        logp_buf = torch.empty((T, N), device=dev)
+        val_buf = torch.empty((T, N), device=dev)
+        rew_buf = torch.empty((T, N), device=dev)
+        done_buf = torch.empty((T, N), dtype=torch.bool, device=dev)
+        start_buf = torch.empty((T, N), dtype=torch.bool, device=dev)
+        init_state = tuple(s.clone() for s in self.state)
+        ep = torch.zeros(4, dtype=torch.float64, device=dev)
+        std = self.policy.log_std.exp()
+        for t in range(T):
+            with torch.no_grad():
+                mean, v, self.state = self.policy.step(self.obs, self.state, self.starts)
+                noise = torch.randn(mean.shape, device=dev, generator=self.gen)
+                a = mean + noise * std
+                logp = (-0.5 * noise.pow(2) - self.policy.log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
+            obs_buf[t], act_buf[t], logp_buf[t], val_buf[t], start_buf[t] = self.obs, a, logp, v, self.starts
+            clipped = torch.minimum(torch.maximum(a, self.low), self.high).float().contiguous()
+            obs, rew, term, trunc, term_obs = env.step_t(clipped)
+            done = term | trunc
+            timeout = (trunc & ~term).float()
+            with torch.no_grad():
+                rew = rew + cfg.gamma * self.policy.peek_value(term_obs, self.state) * timeout
+            rew = torch.nan_to_num(rew, nan=0.0, posinf=0.0, neginf=0.0)
+            if cfg.reward_clip > 0:
+                rew = rew.clamp(-cfg.reward_clip, cfg.reward_clip)
+            rew_buf[t], done_buf[t] = rew, done
+            self._ep_ret += rew
+            self._ep_len += 1
+            d = done.to(torch.float64)
+            ep += torch.stack([(self._ep_ret.double() * d).sum(), (self._ep_len.double() * d).sum(),
+                               (term.double() * d).sum(), d.sum()])
+            keep = (~done).float()
+            self._ep_ret *= keep
+            self._ep_len *= keep
+            self.obs = obs.clone()
+            self.starts = done.clone()
+        with torch.no_grad():
+            _, last_value, _ = self.policy.step(self.obs, self.state, self.starts)
+        adv, ret = compute_gae(rew_buf, val_buf, done_buf, last_value, cfg.gamma, cfg.gae_lambda)
+        self.env_steps += T * N
+        return dict(obs=obs_buf, act=act_buf, logp=logp_buf, val=val_buf, adv=adv, ret=ret, starts=start_buf,
+                    init_state=init_state, mean_reward=rew_buf.mean(), episodes=ep)
+
+    def update(self, roll):
+        cfg = self.cfg
+        T, N = roll["logp"].shape
+        envs_per_mb = max(1, min(N, cfg.batch_size // T))
+        kl = clipf = vl = pl = 0.0
+        count = 0
+        for _ in range(cfg.n_epochs):
+            perm = torch.randperm(N, device=self.device, generator=self.gen)
+            for s in range(0, N - envs_per_mb + 1, envs_per_mb):
+                idx = perm[s:s + envs_per_mb]
+                state = tuple(x[idx] for x in roll["init_state"])
+                means, vals = [], []
+                for t in range(T):                         # BPTT over the rollout, reset at episode starts
+                    m, v, state = self.policy.step(roll["obs"][t, idx], state, roll["starts"][t, idx])
+                    means.append(m)
+                    vals.append(v)
+                mean, val = torch.stack(means), torch.stack(vals)
+                dist = torch.distributions.Normal(mean, self.policy.log_std.exp())
+                logp = dist.log_prob(roll["act"][:, idx]).sum(-1)
+                old_logp = roll["logp"][:, idx]
+                adv = roll["adv"][:, idx]
+                if cfg.normalize_advantage:
+                    adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+                ratio = (logp - old_logp).exp()
+                policy_loss = -torch.minimum(adv * ratio, adv * ratio.clamp(1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
+                value_loss = (roll["ret"][:, idx] - val).pow(2).mean()
+                loss = policy_loss + cfg.vf_coef * value_loss - cfg.ent_coef * dist.entropy().sum(-1).mean()
+                self.opt.zero_grad(set_to_none=True)
+                loss.backward()
+                self._allreduce_grads()
+                nn.utils.clip_grad_norm_(self.policy.parameters(), cfg.max_grad_norm)
+                self.opt.step()
+                with torch.no_grad():
+                    lr = logp - old_logp
+                    kl += float(((lr.exp() - 1) - lr).mean())
+                    clipf += float(((ratio - 1).abs() > cfg.clip_range).float().mean())
+                    vl += float(value_loss)
+                    pl += float(policy_loss)
+                count += 1
+        c = max(count, 1)
+        return dict(approx_kl=kl / c, clip_fraction=clipf / c, value_loss=vl / c, policy_loss=pl / c)

@@ -78,3 +78,39 @@ def test_ppo_improves_on_gpu():
     print("mean step reward: first 5 iterations", first, "last 5", last, "success", h[-1]["success_rate"],
           "env-steps/s incl. learner", stats.env_steps / sum(x["rollout_seconds"] + x["update_seconds"] for x in h))
     assert last > first + 0.5
+
+
+def test_recurrent_policy_resets_state_at_episode_starts():
+    from grasp_lab_salp_b200.ppo import LstmPolicy
+    torch.manual_seed(1)
+    p = LstmPolicy(10, 3)
+    obs = torch.randn(4, 10)
+    s0 = p.initial_state(4, "cpu")
+    _, _, s1 = p.step(obs, s0, torch.ones(4, dtype=torch.bool))
+    starts = torch.tensor([True, False, True, False])
+    m_a, v_a, _ = p.step(obs, s1, starts)
+    m_b, v_b, _ = p.step(obs, s0, torch.ones(4, dtype=torch.bool))       # fresh state everywhere
+    np.testing.assert_allclose(m_a[starts].detach(), m_b[starts].detach(), rtol=1e-6)
+    assert not np.allclose(m_a[~starts].detach(), m_b[~starts].detach())
+    assert sum(x.numel() for x in p.parameters()) > 500_000            # 2 x LSTM(10 -> 256) + heads
+
+
+def test_recurrent_ppo_runs_and_replays_its_rollout():
+    """The update's sequence replay must reproduce the rollout's log-probs and values exactly
+    (before any optimiser step): same LSTM states, same resets."""
+    from emu_backend import EmuBatch
+    from grasp_lab_salp_b200.ppo import RecurrentPPO
+    g = load_golden("ref_random.npz")
+    env = HostEnv(EmuBatch(24, golden_params(g, precision=PRECISION_F64), seed=2))
+    ppo = RecurrentPPO(env, PPOConfig(n_steps=10, n_epochs=1, batch_size=10 * 24, seed=5, learning_rate=0.0))
+    roll = ppo.collect()
+    state = roll["init_state"]
+    for t in range(10):
+        m, v, state = ppo.policy.step(roll["obs"][t], state, roll["starts"][t])
+        lp = torch.distributions.Normal(m, ppo.policy.log_std.exp()).log_prob(roll["act"][t]).sum(-1)
+        np.testing.assert_allclose(lp.detach(), roll["logp"][t], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(v.detach(), roll["val"][t], rtol=1e-4, atol=1e-5)
+    out = ppo.update(roll)
+    assert abs(out["approx_kl"]) < 1e-6 and np.isfinite(out["value_loss"])
+    stats = ppo.learn(ppo.env_steps + 2 * 10 * 24)
+    assert len(stats.history) == 2

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Train PPO (MLP policy, SB3 defaults) on the batched GPU simulator -- BASELINE config 3.
+"""Train PPO (MLP policy, SB3 defaults; --recurrent: LSTM policy of train_robot_recurrent_ppo.py) on the
+batched GPU simulator -- BASELINE configs 3 and 4.
 
     python tools/train_ppo.py --envs 16384 --total-steps 10000000 --out gpurun_out/ppo_curve.jsonl
     torchrun --nproc-per-node 8 tools/train_ppo.py --envs 65536 ...      (envs = whole job, sharded)
@@ -18,7 +19,7 @@ import torch  # noqa: E402
 
 from grasp_lab_salp_b200 import PRECISION_F64, PRECISION_MIXED, default_params  # noqa: E402
 from grasp_lab_salp_b200.distributed import make_shard, world_info  # noqa: E402
-from grasp_lab_salp_b200.ppo import PPO, DeviceEnv, PPOConfig  # noqa: E402
+from grasp_lab_salp_b200.ppo import PPO, DeviceEnv, PPOConfig, RecurrentPPO  # noqa: E402
 
 
 def main():
@@ -30,6 +31,7 @@ def main():
     ap.add_argument("--batch-size", type=int, default=16384)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--precision", choices=["mixed", "f64"], default="mixed")
+    ap.add_argument("--recurrent", action="store_true", help="RecurrentPPO, LSTM(256) actor and critic (config 4)")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     rank, local, world = world_info()
@@ -40,8 +42,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     params = default_params(precision=PRECISION_MIXED if args.precision == "mixed" else PRECISION_F64)
     batch = make_shard(args.envs, params, seed=args.seed)
-    ppo = PPO(DeviceEnv(batch), PPOConfig(n_steps=args.n_steps, n_epochs=args.n_epochs, batch_size=args.batch_size,
-                                          seed=args.seed))
+    algo = RecurrentPPO if args.recurrent else PPO
+    ppo = algo(DeviceEnv(batch), PPOConfig(n_steps=args.n_steps, n_epochs=args.n_epochs, batch_size=args.batch_size,
+                                           seed=args.seed))
     out = open(args.out, "w") if (args.out and rank == 0) else None
     t0 = time.perf_counter()
 
