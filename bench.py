@@ -171,7 +171,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -421,7 +421,7 @@ def run_cuda_arm(args):
             line["cpu_baseline"] = cpu
         if sweep:
             line["sweep"] = sweep
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -445,8 +445,23 @@ def state_bytes_per_env_step(params):
     return 2 * cols + 12 + (2 * D * 4 + 4 + 2 + 4)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the process's original stdout; everything else any library
+    prints (NCCL's version banner, torchrun notices) has been rerouted to stderr."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
         return
