@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""Long-horizon trajectory equivalence on the GPU -- BASELINE config 2:
+4096 batched envs, uniform-random actions, 10 000 env-steps, fp32 production kernel vs the
+float64 reference-mode kernel, FREE-RUNNING (no re-synchronisation unless a termination flag
+differs, in which case that env is re-synchronised from the float64 run and counted).
+
+Metrics follow the reference's compare_trajectories.py (src/compare_trajectories.py:64-86):
+state tuple (x, y, vx, vy, yaw, yaw-rate); position error = L2 of (x, y), velocity error = L2 of
+(vx, vy), yaw error = |d yaw|; mean and max over envs, reported per checkpoint and overall.
+Integer quantities (K, cycle, phase, done/truncated, reset indices) must agree exactly.
+
+    python tools/compare_trajectories.py --envs 4096 --steps 10000 --out gpurun_out/traj_equiv.json
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from grasp_lab_salp_b200 import PRECISION_F64, PRECISION_MIXED, SalpBatch, default_params  # noqa: E402
+from grasp_lab_salp_b200.params import FIELDS  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=4096)
+    ap.add_argument("--steps", type=int, default=10000)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    n, T = args.envs, args.steps
+    dev = torch.device("cuda", 0)
+    mixed = SalpBatch(n, default_params(precision=PRECISION_MIXED), seed=args.seed)
+    f64 = SalpBatch(n, default_params(precision=PRECISION_F64), seed=args.seed)
+    mixed.reset_device()
+    f64.reset_device()
+    cols = ["posw_x", "posw_y", "vel_x", "vel_y", "euler_z", "angvel_z"]
+    tm = {c: mixed.state_tensor(c) for c in cols}
+    tf = {c: f64.state_tensor(c) for c in cols}
+    sync_cols = [c for c in FIELDS if not (c.startswith("obstacle") and int(c[8]) >= 2)]
+    sm = {c: mixed.state_tensor(c) for c in sync_cols}
+    sf = {c: f64.state_tensor(c) for c in sync_cols}
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + args.seed)
+    acc = dict(pos_max=0.0, vel_max=0.0, yaw_max=0.0, pos_sum=0.0, vel_sum=0.0, yaw_sum=0.0, count=0)
+    flag_mismatch = k_mismatch = resyncs = episodes = blowups = 0
+    checkpoints = []
+    t0 = time.perf_counter()
+    for t in range(T):
+        a = torch.rand((n, 3), generator=g, device=dev)
+        a[:, 2] = a[:, 2] * 2 - 1
+        om, rm, tem, trm = mixed.step_device(a, auto_reset=True)
+        of, rf, tef, trf = f64.step_device(a, auto_reset=True)
+        k_bad = mixed.dev["substeps"] != f64.dev["substeps"]
+        bad = (tem != tef) | (trm != trf)
+        ended = (tef | trf).bool()
+        # compare the state of envs that did NOT just reset (after a reset both are exactly at rest)
+        live = ~ended & ~bad
+        pos = torch.hypot(tm["posw_x"] - tf["posw_x"], tm["posw_y"] - tf["posw_y"])[live]
+        vel = torch.hypot(tm["vel_x"] - tf["vel_x"], tm["vel_y"] - tf["vel_y"])[live]
+        yaw = (tm["euler_z"] - tf["euler_z"]).abs()[live]
+        fin = torch.isfinite(pos) & torch.isfinite(vel) & torch.isfinite(yaw)
+        pos, vel, yaw = pos[fin], vel[fin], yaw[fin]
+        acc["pos_max"] = max(acc["pos_max"], float(pos.max()))
+        acc["vel_max"] = max(acc["vel_max"], float(vel.max()))
+        acc["yaw_max"] = max(acc["yaw_max"], float(yaw.max()))
+        acc["pos_sum"] += float(pos.sum()); acc["vel_sum"] += float(vel.sum()); acc["yaw_sum"] += float(yaw.sum())
+        acc["count"] += int(pos.numel())
+        flag_mismatch += int(bad.sum())
+        k_mismatch += int(k_bad.sum())
+        episodes += int(ended.sum())
+        if bool(bad.any()):
+            resyncs += int(bad.sum())
+            for c in sync_cols:
+                sm[c][bad] = sf[c][bad]
+            mixed.dev["obs"][bad] = f64.dev["obs"][bad]
+        if (t + 1) % max(1, T // 10) == 0:
+            checkpoints.append(dict(step=t + 1, pos_mean=acc["pos_sum"] / acc["count"], pos_max=acc["pos_max"],
+                                    vel_max=acc["vel_max"], yaw_max=acc["yaw_max"], flag_mismatch=flag_mismatch,
+                                    max_cycle=int(sf["cycle"].max())))
+            print(json.dumps(checkpoints[-1]), flush=True)
+    mixed.check()
+    f64.check()
+    c = max(acc["count"], 1)
+    out = dict(envs=n, steps=T, env_steps=n * T, episodes=episodes, wall_seconds=time.perf_counter() - t0,
+               substep_count_mismatches=k_mismatch, flag_mismatches=flag_mismatch, resynchronised_envs=resyncs,
+               position_error_m=dict(mean=acc["pos_sum"] / c, max=acc["pos_max"]),
+               velocity_error_m_s=dict(mean=acc["vel_sum"] / c, max=acc["vel_max"]),
+               yaw_error_rad=dict(mean=acc["yaw_sum"] / c, max=acc["yaw_max"]), checkpoints=checkpoints,
+               note="fp32 production kernel vs float64 reference-mode kernel, free-running; errors over envs that are "
+                    "mid-episode in both runs; an env whose done/truncated flag differs is re-synchronised and counted")
+    print(json.dumps({k: v for k, v in out.items() if k != "checkpoints"}, indent=1))
+    if args.out:
+        with open(args.out, "w") as f:
+            json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
