@@ -265,7 +265,6 @@ struct Motion32 {
   // (sin/cos of roll and pitch are carried: the Euler-rate matrix uses the OLD angles)
   float phi_lo, theta_lo, psi_lo;
   float sph, cph, sth, cth, sps, cps;
-  float rcth;                            // 1 / cos(pitch): Newton-refined from the previous substep's value
   float pw0, pw1, pw2;                   // chunk partial sums: position_world, position, angle
   float pos0, pos1, pos2, ang0, ang1, ang2;
   float vw0, vw1;                        // velocity_world[0:2] of the latest kinematic update
@@ -298,7 +297,13 @@ SALP_HD void dyn_step(const SalpDerived& dv, const Coef32& g, Motion32& s) {
 // roll/pitch (dynamics.py:21-31), new angles, body->world rotation Rz Ry Rx (dynamics.py:35-58) by
 // successive elementary rotations, the three position/angle integrals.  ~65 FP32 instructions.
 // v, w are the velocities AFTER dyn_step of the same substep.
-SALP_HD void rotate_small(float d, float& sn, float& cs) {     // (sin, cos)(x) -> (sin, cos)(x + d), |d| <= 0.55
+// (sin, cos)(x) -> (sin, cos)(x + d).  The Taylor kernels are valid for |d| <= 0.55 (a substep moves an
+// Euler angle by ~1e-2 rad); a tumbling body passing the pitch = +-pi/2 singularity of the Euler-rate
+// matrix (long random episodes do, in the reference too) can ask for more for a substep or two:
+// the increment is clamped so that the pair stays a unit vector, and the true angle -- which keeps
+// accumulating the unclamped increment -- re-anchors it at the next flush.
+SALP_HD void rotate_small(float d, float& sn, float& cs) {
+  d = fminf(fmaxf(d, -0.55f), 0.55f);
   float sd_, cd_;
   sincos_small(d, sd_, cd_);
   float ns = sn * cd_ + cs * sd_;
@@ -308,7 +313,7 @@ SALP_HD void rotate_small(float d, float& sn, float& cs) {     // (sin, cos)(x) 
 SALP_HD void kin_step(const SalpDerived& dv, Motion32& s) {
   const float dt = dv.dt;
   const float v0 = s.v0, v1 = s.v1, v2 = s.v2, w0 = s.w0, w1 = s.w1, w2 = s.w2;
-  const float rcth = s.rcth;
+  const float rcth = fast_rcp(s.cth);          // (not Newton-carried: cos(pitch) changes sign when the body tumbles)
   float q = s.sph * w1 + s.cph * w2;
   float dphi = fmaf(s.sth * rcth, q, w0) * dt;
   float dtheta = (s.cph * w1 - s.sph * w2) * dt;
@@ -319,11 +324,6 @@ SALP_HD void kin_step(const SalpDerived& dv, Motion32& s) {
   rotate_small(dphi, s.sph, s.cph);
   rotate_small(dtheta, s.sth, s.cth);
   rotate_small(dpsi, s.sps, s.cps);
-  // 1 / cos(pitch) for the next substep: cos(pitch) moved by O(1e-4) relative, so two Newton steps
-  // from the previous reciprocal are exact to fp32 (re-seeded from MUFU.RCP at every flush)
-  float r = s.rcth;
-  r = r * fmaf(-s.cth, r, 2.0f);
-  s.rcth = r * fmaf(-s.cth, r, 2.0f);
   float u1 = s.cph * v1 - s.sph * v2, u2 = s.sph * v1 + s.cph * v2;      // Rx
   float r0 = s.cth * v0 + s.sth * u2, vw2 = s.cth * u2 - s.sth * v0;     // Ry
   s.vw0 = s.cps * r0 - s.sps * u1;                                       // Rz
@@ -354,7 +354,6 @@ SALP_HD void flush_chunk(Body64& b, Motion32& s) {
   anchor_sincos(b.eul[0], s.sph, s.cph);
   anchor_sincos(b.eul[1], s.sth, s.cth);
   anchor_sincos(b.eul[2], s.sps, s.cps);
-  s.rcth = fast_rcp(s.cth);
   s.phi_lo = s.theta_lo = s.psi_lo = 0.f;
   s.pw0 = s.pw1 = s.pw2 = 0.f;
   s.pos0 = s.pos1 = s.pos2 = 0.f;
@@ -427,7 +426,6 @@ SALP_HD void mixed_init_kin(const Body64& b, Motion32& s) {
   anchor_sincos(b.eul[0], s.sph, s.cph);
   anchor_sincos(b.eul[1], s.sth, s.cth);
   anchor_sincos(b.eul[2], s.sps, s.cps);
-  s.rcth = fast_rcp(s.cth);
   s.phi_lo = s.theta_lo = s.psi_lo = 0.f;
   s.pw0 = s.pw1 = s.pw2 = 0.f;
   s.pos0 = s.pos1 = s.pos2 = 0.f; s.ang0 = s.ang1 = s.ang2 = 0.f;
