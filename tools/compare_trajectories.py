@@ -38,7 +38,7 @@ def main():
     f64 = SalpBatch(n, default_params(precision=PRECISION_F64), seed=args.seed)
     mixed.reset_device()
     f64.reset_device()
-    cols = ["posw_x", "posw_y", "vel_x", "vel_y", "euler_z", "angvel_z"]
+    cols = ["posw_x", "posw_y", "vel_x", "vel_y", "euler_z", "angvel_z", "euler_x", "euler_y"]
     tm = {c: mixed.state_tensor(c) for c in cols}
     tf = {c: f64.state_tensor(c) for c in cols}
     sync_cols = [c for c in FIELDS if not (c.startswith("obstacle") and int(c[8]) >= 2)]
@@ -47,19 +47,27 @@ def main():
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + args.seed)
     acc = dict(pos_max=0.0, vel_max=0.0, yaw_max=0.0, pos_sum=0.0, vel_sum=0.0, yaw_sum=0.0, count=0)
-    flag_mismatch = k_mismatch = resyncs = episodes = blowups = 0
+    flag_mismatch = k_mismatch = resyncs = episodes = 0
+    flag_mismatch_regular = tumbling_env_steps = regular_env_steps = 0
     checkpoints = []
     t0 = time.perf_counter()
     for t in range(T):
         a = torch.rand((n, 3), generator=g, device=dev)
         a[:, 2] = a[:, 2] * 2 - 1
+        # A long random episode eventually TUMBLES (|roll|, |pitch| grow past 1 rad after ~200 cycles,
+        # in the float64 model too): that regime is chaotic, any two roundings diverge within a few
+        # cycles, so it is reported separately from the regular regime the tolerance speaks about.
+        tumbling = (tf["euler_x"].abs() > 0.3) | (tf["euler_y"].abs() > 0.3)
         om, rm, tem, trm = mixed.step_device(a, auto_reset=True)
         of, rf, tef, trf = f64.step_device(a, auto_reset=True)
         k_bad = mixed.dev["substeps"] != f64.dev["substeps"]
         bad = (tem != tef) | (trm != trf)
         ended = (tef | trf).bool()
         # compare the state of envs that did NOT just reset (after a reset both are exactly at rest)
-        live = ~ended & ~bad
+        live = ~ended & ~bad & ~tumbling
+        tumbling_env_steps += int(tumbling.sum())
+        regular_env_steps += int((~tumbling).sum())
+        flag_mismatch_regular += int((bad & ~tumbling).sum())
         pos = torch.hypot(tm["posw_x"] - tf["posw_x"], tm["posw_y"] - tf["posw_y"])[live]
         vel = torch.hypot(tm["vel_x"] - tf["vel_x"], tm["vel_y"] - tf["vel_y"])[live]
         yaw = (tm["euler_z"] - tf["euler_z"]).abs()[live]
@@ -81,6 +89,7 @@ def main():
         if (t + 1) % max(1, T // 10) == 0:
             checkpoints.append(dict(step=t + 1, pos_mean=acc["pos_sum"] / acc["count"], pos_max=acc["pos_max"],
                                     vel_max=acc["vel_max"], yaw_max=acc["yaw_max"], flag_mismatch=flag_mismatch,
+                                    flag_mismatch_regular=flag_mismatch_regular,
                                     max_cycle=int(sf["cycle"].max())))
             print(json.dumps(checkpoints[-1]), flush=True)
     mixed.check()
@@ -88,11 +97,15 @@ def main():
     c = max(acc["count"], 1)
     out = dict(envs=n, steps=T, env_steps=n * T, episodes=episodes, wall_seconds=time.perf_counter() - t0,
                substep_count_mismatches=k_mismatch, flag_mismatches=flag_mismatch, resynchronised_envs=resyncs,
+               regular_env_steps=regular_env_steps, tumbling_env_steps=tumbling_env_steps,
+               flag_mismatches_regular=flag_mismatch_regular,
+               flag_mismatches_tumbling=flag_mismatch - flag_mismatch_regular,
                position_error_m=dict(mean=acc["pos_sum"] / c, max=acc["pos_max"]),
                velocity_error_m_s=dict(mean=acc["vel_sum"] / c, max=acc["vel_max"]),
                yaw_error_rad=dict(mean=acc["yaw_sum"] / c, max=acc["yaw_max"]), checkpoints=checkpoints,
                note="fp32 production kernel vs float64 reference-mode kernel, free-running; errors over envs that are "
-                    "mid-episode in both runs; an env whose done/truncated flag differs is re-synchronised and counted")
+                    "mid-episode in both runs and not tumbling (|roll|, |pitch| <= 0.3 rad in the float64 run); an env "
+                    "whose done/truncated flag differs is re-synchronised and counted")
     print(json.dumps({k: v for k, v in out.items() if k != "checkpoints"}, indent=1))
     if args.out:
         with open(args.out, "w") as f:
