@@ -135,6 +135,7 @@ class PPOConfig:
                                       # reference env returns finite but astronomically large rewards for cycles next
                                       # to its integrator's stability limit, which would destroy any
                                       # value function; set to 0 to disable
+    cuda_graphs: bool = False         # MLP PPO on CUDA: replay the whole rollout and each minibatch step as CUDA graphs
     seed: int = 0
     hidden: tuple = (64, 64)
     action_low: tuple = (0.0, 0.0, -1.0)     # the Box of salp_robot_env.py:63-67
@@ -181,7 +182,12 @@ class PPO:
         self.device = env.device
         torch.manual_seed(self.cfg.seed)
         self.policy = (policy or MlpPolicy(env.obs_dim, 3, self.cfg.hidden)).to(self.device)
-        self.opt = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.learning_rate, eps=1e-5)
+        self.use_graphs = bool(self.cfg.cuda_graphs) and self.device.type == "cuda"
+        self.opt = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.learning_rate, eps=1e-5,
+                                    capturable=self.use_graphs)
+        self.graph_update = self.use_graphs
+        self._roll_graph = self._upd_graph = None
+        self._roll_calls = self._upd_calls = 0
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(self.cfg.seed + 1)
         self.low = torch.tensor(self.cfg.action_low, device=self.device)
@@ -199,24 +205,29 @@ class PPO:
                 self.dist_world = dist.get_world_size()
                 for p in self.policy.parameters():          # identical initial weights on every rank
                     dist.broadcast(p.data, src=0)
+                self.graph_update = False                   # (the NCCL all-reduce stays outside CUDA graphs)
         except Exception:
             pass
 
     # ---- rollout ----
-    def collect(self):
-        cfg, env, T, N = self.cfg, self.env, self.cfg.n_steps, self.env.num_envs
-        dev = self.device
-        obs_buf = torch.empty((T, N, env.obs_dim), device=dev)
-        act_buf = torch.empty((T, N, 3), device=dev)
-        logp_buf = torch.empty((T, N), device=dev)
-        val_buf = torch.empty((T, N), device=dev)
-        rew_buf = torch.empty((T, N), device=dev)
-        done_buf = torch.empty((T, N), dtype=torch.bool, device=dev)
-        # episode statistics as masked device-side sums: no host synchronisation inside the rollout
-        ep = torch.zeros(4, dtype=torch.float64, device=dev)       # [sum return, sum length, successes, episodes]
+    def _alloc_rollout(self):
+        env, T, N, dev = self.env, self.cfg.n_steps, self.env.num_envs, self.device
+        self._rb = dict(obs=torch.empty((T, N, env.obs_dim), device=dev), act=torch.empty((T, N, 3), device=dev),
+                        logp=torch.empty((T, N), device=dev), val=torch.empty((T, N), device=dev),
+                        rew=torch.empty((T, N), device=dev), done=torch.empty((T, N), dtype=torch.bool, device=dev),
+                        adv=torch.empty((T, N), device=dev), ret=torch.empty((T, N), device=dev),
+                        ep=torch.zeros(4, dtype=torch.float64, device=dev), mean_reward=torch.zeros((), device=dev))
+
+    def _rollout_body(self):
+        """T env-steps + GAE, everything in place on persistent device buffers (so that the whole
+        body can be captured once and replayed as ONE CUDA graph: policy forward, salp_step and the
+        bookkeeping of all T steps, no host round trip)."""
+        cfg, env, T, rb = self.cfg, self.env, self.cfg.n_steps, self._rb
+        ep = rb["ep"]            # [sum return, sum length, successes, episodes] of the episodes that ended
+        ep.zero_()
         for t in range(T):
             a, logp, v = self.policy.act(self.obs, self.gen)
-            obs_buf[t], act_buf[t], logp_buf[t], val_buf[t] = self.obs, a, logp, v
+            rb["obs"][t].copy_(self.obs); rb["act"][t].copy_(a); rb["logp"][t].copy_(logp); rb["val"][t].copy_(v)
             clipped = torch.minimum(torch.maximum(a, self.low), self.high).float().contiguous()
             obs, rew, term, trunc, term_obs = env.step_t(clipped)
             done = term | trunc
@@ -226,7 +237,7 @@ class PPO:
             rew = torch.nan_to_num(rew, nan=0.0, posinf=0.0, neginf=0.0)
             if cfg.reward_clip > 0:
                 rew = rew.clamp(-cfg.reward_clip, cfg.reward_clip)
-            rew_buf[t], done_buf[t] = rew, done
+            rb["rew"][t].copy_(rew); rb["done"][t].copy_(done)
             self._ep_ret += rew
             self._ep_len += 1
             d = done.to(torch.float64)
@@ -235,15 +246,33 @@ class PPO:
             keep = (~done).float()
             self._ep_ret *= keep
             self._ep_len *= keep
-            self.obs = obs.clone()
+            self.obs.copy_(obs)
         with torch.no_grad():
             last_value = self.policy.value(self.obs)
-        adv, ret = compute_gae(rew_buf, val_buf, done_buf, last_value, cfg.gamma, cfg.gae_lambda)
+        adv, ret = compute_gae(rb["rew"], rb["val"], rb["done"], last_value, cfg.gamma, cfg.gae_lambda)
+        rb["adv"].copy_(adv); rb["ret"].copy_(ret)
+        rb["mean_reward"].copy_(rb["rew"].mean())
+
+    def collect(self):
+        T, N = self.cfg.n_steps, self.env.num_envs
+        if not hasattr(self, "_rb"):
+            self._alloc_rollout()
+        self._roll_calls += 1
+        if self.use_graphs and self._roll_calls >= 2:
+            if self._roll_graph is None:          # the first rollout ran eagerly (warm-up); capture now
+                g = torch.cuda.CUDAGraph()
+                g.register_generator_state(self.gen)
+                with torch.cuda.graph(g):
+                    self._rollout_body()
+                self._roll_graph = g
+            self._roll_graph.replay()
+        else:
+            self._rollout_body()
         self.env_steps += T * N
-        episodes = ep
+        rb = self._rb
         flat = lambda x: x.reshape(T * N, *x.shape[2:])  # noqa: E731
-        return dict(obs=flat(obs_buf), act=flat(act_buf), logp=flat(logp_buf), val=flat(val_buf), adv=flat(adv),
-                    ret=flat(ret), mean_reward=rew_buf.mean(), episodes=episodes)
+        return dict(obs=flat(rb["obs"]), act=flat(rb["act"]), logp=flat(rb["logp"]), val=flat(rb["val"]),
+                    adv=flat(rb["adv"]), ret=flat(rb["ret"]), mean_reward=rb["mean_reward"], episodes=rb["ep"])
 
     # ---- update ----
     def _allreduce_grads(self):
@@ -259,39 +288,56 @@ class PPO:
             g.copy_(flat[off:off + g.numel()].view_as(g))
             off += g.numel()
 
+    def _minibatch_step(self, roll, idx, stats):
+        cfg = self.cfg
+        adv = roll["adv"][idx]
+        if cfg.normalize_advantage:
+            adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+        logp, ent, val = self.policy.evaluate(roll["obs"][idx], roll["act"][idx])
+        old = roll["logp"][idx]
+        ratio = (logp - old).exp()
+        p1, p2 = adv * ratio, adv * ratio.clamp(1 - cfg.clip_range, 1 + cfg.clip_range)
+        policy_loss = -torch.minimum(p1, p2).mean()
+        value_loss = (roll["ret"][idx] - val).pow(2).mean()
+        loss = policy_loss + cfg.vf_coef * value_loss - cfg.ent_coef * ent.mean()
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        self._allreduce_grads()
+        nn.utils.clip_grad_norm_(self.policy.parameters(), cfg.max_grad_norm)
+        self.opt.step()
+        with torch.no_grad():                     # statistics stay on the device (one read-back per update)
+            lr = logp - old
+            stats += torch.stack([((lr.exp() - 1) - lr).mean(), ((ratio - 1).abs() > cfg.clip_range).float().mean(),
+                                  value_loss.detach(), policy_loss.detach()])
+
     def update(self, roll):
         cfg = self.cfg
         n = roll["obs"].shape[0]
         bs = min(cfg.batch_size, n)
-        kl = clipf = vl = pl = 0.0
+        stats = getattr(self, "_upd_stats", None)
+        if stats is None:
+            stats = self._upd_stats = torch.zeros(4, device=self.device)
+            self._upd_idx = torch.zeros(bs, dtype=torch.long, device=self.device)
+        stats.zero_()
         count = 0
         for _ in range(cfg.n_epochs):
             perm = torch.randperm(n, device=self.device, generator=self.gen)
             for s in range(0, n - bs + 1, bs):
-                idx = perm[s:s + bs]
-                adv = roll["adv"][idx]
-                if cfg.normalize_advantage:
-                    adv = (adv - adv.mean()) / (adv.std() + 1e-8)
-                logp, ent, val = self.policy.evaluate(roll["obs"][idx], roll["act"][idx])
-                ratio = (logp - roll["logp"][idx]).exp()
-                p1, p2 = adv * ratio, adv * ratio.clamp(1 - cfg.clip_range, 1 + cfg.clip_range)
-                policy_loss = -torch.minimum(p1, p2).mean()
-                value_loss = (roll["ret"][idx] - val).pow(2).mean()
-                loss = policy_loss + cfg.vf_coef * value_loss - cfg.ent_coef * ent.mean()
-                self.opt.zero_grad(set_to_none=True)
-                loss.backward()
-                self._allreduce_grads()
-                nn.utils.clip_grad_norm_(self.policy.parameters(), cfg.max_grad_norm)
-                self.opt.step()
-                with torch.no_grad():
-                    lr = logp - roll["logp"][idx]
-                    kl += float(((lr.exp() - 1) - lr).mean())
-                    clipf += float(((ratio - 1).abs() > cfg.clip_range).float().mean())
-                    vl += float(value_loss)
-                    pl += float(policy_loss)
+                self._upd_idx.copy_(perm[s:s + bs])
+                self._upd_calls += 1
+                if self.graph_update and self._upd_calls > 3:
+                    if self._upd_graph is None:   # three eager (real) steps warmed everything up; capture the 4th
+                        self.opt.zero_grad(set_to_none=True)
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            self._minibatch_step(roll, self._upd_idx, stats)
+                        self._upd_graph = g
+                    self._upd_graph.replay()
+                else:
+                    self._minibatch_step(roll, self._upd_idx, stats)
                 count += 1
-        c = max(count, 1)
-        return dict(approx_kl=kl / c, clip_fraction=clipf / c, value_loss=vl / c, policy_loss=pl / c)
+        kl, clipf, vl, pl = (stats / max(count, 1)).tolist()
+        return dict(approx_kl=kl, clip_fraction=clipf, value_loss=vl, policy_loss=pl)
 
     def _reduce_stat(self, total, count):
         if self.dist_world > 1:

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--precision", choices=["mixed", "f64"], default="mixed")
     ap.add_argument("--recurrent", action="store_true", help="RecurrentPPO, LSTM(256) actor and critic (config 4)")
+    ap.add_argument("--cuda-graphs", action="store_true", help="replay rollout and minibatch steps as CUDA graphs")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     rank, local, world = world_info()
@@ -44,7 +45,7 @@ def main():
     batch = make_shard(args.envs, params, seed=args.seed)
     algo = RecurrentPPO if args.recurrent else PPO
     ppo = algo(DeviceEnv(batch), PPOConfig(n_steps=args.n_steps, n_epochs=args.n_epochs, batch_size=args.batch_size,
-                                           seed=args.seed))
+                                           seed=args.seed, cuda_graphs=args.cuda_graphs))
     out = open(args.out, "w") if (args.out and rank == 0) else None
     t0 = time.perf_counter()
 
