@@ -97,7 +97,7 @@ class MlpPolicy(nn.Module):
         self.log_std = nn.Parameter(torch.full((act_dim,), float(log_std_init)))
 
     def dist(self, obs):
-        return torch.distributions.Normal(self.actor(obs), self.log_std.exp())
+        return torch.distributions.Normal(self.actor(obs), self.log_std.exp(), validate_args=False)
 
     def value(self, obs):
         return self.critic(obs).squeeze(-1)
@@ -111,8 +111,13 @@ class MlpPolicy(nn.Module):
         return a, logp, self.value(obs)
 
     def evaluate(self, obs, actions):
-        d = self.dist(obs)
-        return d.log_prob(actions).sum(-1), d.entropy().sum(-1), self.value(obs)
+        """log-prob, entropy, value -- written out (no torch.distributions: its argument validation
+        synchronises the stream, which also forbids CUDA-graph capture)."""
+        mean = self.actor(obs)
+        z = (actions - mean) * (-self.log_std).exp()
+        logp = (-0.5 * z.pow(2) - self.log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
+        ent = (0.5 + 0.5 * math.log(2 * math.pi) + self.log_std).sum().expand(obs.shape[0])
+        return logp, ent, self.value(obs)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -489,7 +494,7 @@ class RecurrentPPO(PPO):
                     means.append(m)
                     vals.append(v)
                 mean, val = torch.stack(means), torch.stack(vals)
-                dist = torch.distributions.Normal(mean, self.policy.log_std.exp())
+                dist = torch.distributions.Normal(mean, self.policy.log_std.exp(), validate_args=False)
                 logp = dist.log_prob(roll["act"][:, idx]).sum(-1)
                 old_logp = roll["logp"][:, idx]
                 adv = roll["adv"][:, idx]
