@@ -394,17 +394,15 @@ SALP_HD void env_step_end(const SalpParams& p, const SalpView& v, const SalpStep
   if ((flags & SALP_STEP_AUTORESET) && ended) env_reset(p, v, i, obs);
 }
 
-// tot_tile / tot_stride: optional shared-memory column for the fp64 totals of the mixed loop
-// (nullptr = thread-local), see flush_chunk.
 template <int PREC>
 SALP_HD void env_step(const SalpParams& p, const SalpDerived& dv, const SalpView& v, const SalpStepIO& io,
-                      uint32_t flags, int64_t i, double* tot_tile = nullptr, int tot_stride = 1) {
+                      uint32_t flags, int64_t i) {
   StepCtx cx;
   Body64 b;
   env_step_begin(p, v, io, i, cx, b);
   const double pos0[3] = {b.pos[0], b.pos[1], b.pos[2]};
   const double ang0[3] = {b.ang[0], b.ang[1], b.ang[2]};
   double t = 0.0;
-  const int K = run_cycle<PREC>(p, dv, cx.plan, v.time_table, b, t, tot_tile, tot_stride);
+  const int K = run_cycle<PREC>(p, dv, cx.plan, v.time_table, b, t);
   env_step_end(p, v, io, flags, i, cx, pos0, ang0, b, K, t);
 }

@@ -158,16 +158,13 @@ SALP_DEV void substep_f64(const SalpParams& p, const CyclePlan& c, Body64& b, do
 struct SalpDerived;   // host-derived constants of the mixed loop (salp_loop_mixed.cuh); unused here
 template <int PREC>
 SALP_HD int run_cycle(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c, const double* time_table,
-                      Body64& b, double& t, double* tot_tile, int tot_stride);
+                      Body64& b, double& t);
 
 template <>
 SALP_HD int run_cycle<SALP_PRECISION_F64>(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c,
-                                          const double* time_table, Body64& b, double& t, double* tot_tile,
-                                          int tot_stride) {
+                                          const double* time_table, Body64& b, double& t) {
   (void)time_table;
   (void)dv;
-  (void)tot_tile;
-  (void)tot_stride;
   refresh_shape_f64(p, b);
   b.mass_rate = (b.water_mass - b.prev_volume * p.density) / p.dt;
   t = 0.0;

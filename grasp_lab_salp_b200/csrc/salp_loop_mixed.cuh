@@ -345,39 +345,19 @@ SALP_HD void anchor_sincos(double x, float& sn, float& cs) {
   cs = fmaf(-s, lo, c);
 }
 
-// fold the fp32 chunk partials into the fp64 totals and re-anchor the three (sin, cos) pairs.
-// The 12 totals (position_world, position, angle, euler) are touched only here, once per 16
-// substeps: `tot` is either a thread-local array (registers: the latency build) or a column of a
-// shared-memory tile (`tot[i * stride]`: the throughput build, whose 128-register budget would
-// otherwise spill them to local memory, i.e. to L2 latency).
-SALP_HD void flush_chunk(double* tot, int stride, Motion32& s) {
-  tot[0 * stride] += (double)s.pw0; tot[1 * stride] += (double)s.pw1; tot[2 * stride] += (double)s.pw2;
-  tot[3 * stride] += (double)s.pos0; tot[4 * stride] += (double)s.pos1; tot[5 * stride] += (double)s.pos2;
-  tot[6 * stride] += (double)s.ang0; tot[7 * stride] += (double)s.ang1; tot[8 * stride] += (double)s.ang2;
-  const double e0 = tot[9 * stride] + (double)s.phi_lo, e1 = tot[10 * stride] + (double)s.theta_lo,
-               e2 = tot[11 * stride] + (double)s.psi_lo;
-  tot[9 * stride] = e0; tot[10 * stride] = e1; tot[11 * stride] = e2;
-  anchor_sincos(e0, s.sph, s.cph);
-  anchor_sincos(e1, s.sth, s.cth);
-  anchor_sincos(e2, s.sps, s.cps);
+// fold the fp32 chunk partials into the fp64 totals and re-anchor the three (sin, cos) pairs
+SALP_HD void flush_chunk(Body64& b, Motion32& s) {
+  b.pw[0] += (double)s.pw0; b.pw[1] += (double)s.pw1; b.pw[2] += (double)s.pw2;
+  b.pos[0] += (double)s.pos0; b.pos[1] += (double)s.pos1; b.pos[2] += (double)s.pos2;
+  b.ang[0] += (double)s.ang0; b.ang[1] += (double)s.ang1; b.ang[2] += (double)s.ang2;
+  b.eul[0] += (double)s.phi_lo; b.eul[1] += (double)s.theta_lo; b.eul[2] += (double)s.psi_lo;
+  anchor_sincos(b.eul[0], s.sph, s.cph);
+  anchor_sincos(b.eul[1], s.sth, s.cth);
+  anchor_sincos(b.eul[2], s.sps, s.cps);
   s.phi_lo = s.theta_lo = s.psi_lo = 0.f;
   s.pw0 = s.pw1 = s.pw2 = 0.f;
   s.pos0 = s.pos1 = s.pos2 = 0.f;
   s.ang0 = s.ang1 = s.ang2 = 0.f;
-}
-SALP_HD void totals_load(const Body64& b, double* tot, int stride) {
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    tot[k * stride] = b.pw[k]; tot[(3 + k) * stride] = b.pos[k];
-    tot[(6 + k) * stride] = b.ang[k]; tot[(9 + k) * stride] = b.eul[k];
-  }
-}
-SALP_HD void totals_store(const double* tot, int stride, Body64& b) {
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    b.pw[k] = tot[k * stride]; b.pos[k] = tot[(3 + k) * stride];
-    b.ang[k] = tot[(6 + k) * stride]; b.eul[k] = tot[(9 + k) * stride];
-  }
 }
 
 // Shape bookkeeping in fp64 (everything the reference differences) + the fp32 coefficient set.
@@ -495,8 +475,7 @@ SALP_HD int next_update_after(int j, const PhasePlan& pp) {
 
 template <>
 SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c,
-                                            const double* time_table, Body64& b, double& t_out, double* tot_tile,
-                                            int tot_stride) {
+                                            const double* time_table, Body64& b, double& t_out) {
   // ---- K: first k with !(t_k < total) in the dtype the reference compares in (robot.py:756) ----
   const int K = plan_substeps(c, time_table);
   t_out = 0.0;
@@ -510,10 +489,6 @@ SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDeriv
   mixed_init_shape(p, dv, b, dir, st, g);
   mixed_init_dyn(b, s);
   mixed_init_kin(b, s);
-  double tot_local[12];
-  double* const tot = tot_tile ? tot_tile : tot_local;
-  const int stride = tot_tile ? tot_stride : 1;
-  totals_load(b, tot, stride);
 
   // The kinematic update of substep k-1 only READS the (v, w) that the dynamics of substep k also
   // only reads, so the loop runs kin(k-1) side by side with dyn(k): two independent dependency
@@ -549,12 +524,11 @@ SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDeriv
       kin_step(dv, s);
       dyn_step(dv, g, s);
     }
-    if (k == boundary) flush_chunk(tot, stride, s);       // two-level sums (fp32 chunk partials -> fp64 totals)
+    if (k == boundary) flush_chunk(b, s);       // two-level sums (fp32 chunk partials -> fp64 totals)
   }
   // ---- the last substep's kinematic update ----
   kin_step(dv, s);
-  flush_chunk(tot, stride, s);
-  totals_store(tot, stride, b);
+  flush_chunk(b, s);
 
   // ---- epilogue: back to the carried fp64 columns ----
   const double tK = time_table[K];

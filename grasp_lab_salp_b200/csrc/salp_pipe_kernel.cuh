@@ -171,8 +171,6 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
     // ---------------- kin warp: Euler angles, world position, body-frame integrals ----------------
     Motion32 s;
     mixed_init_kin(b, s);
-    double tot[12];
-    totals_load(b, tot, 1);
     for (int c = 0; c < nchunks; c++) {
       const int bsel = c & 1;
       pipe_bar_sync(PIPE_FULL_B(bsel));
@@ -185,10 +183,9 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
           kin_step(dv, s);
         }
       }
-      if (c * C < K) flush_chunk(tot, 1, s);
+      if (c * C < K) flush_chunk(b, s);
       pipe_bar_arrive(PIPE_EMPTY_B(bsel));
     }
-    totals_store(tot, 1, b);
     if (K > 0) b.speed_world = (double)sqrtf(s.vw0 * s.vw0 + s.vw1 * s.vw1);
 #pragma unroll
     for (int k = 0; k < 3; k++) {

@@ -24,11 +24,10 @@ __global__ void __launch_bounds__(128, 4)
 salp_step_kernel(const __grid_constant__ SalpParams p, const __grid_constant__ SalpDerived dv,
                  const __grid_constant__ SalpView v, const __grid_constant__ SalpStepIO io, uint32_t flags,
                  const int32_t* __restrict__ order) {
-  __shared__ double tot_tile[12 * 128];          // fp64 totals of the mixed loop, one column per thread
   int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= v.n) return;
   int64_t i = order ? (int64_t)order[tid] : tid;
-  env_step<PREC>(p, dv, v, io, flags, i, tot_tile + threadIdx.x, 128);
+  env_step<PREC>(p, dv, v, io, flags, i);
 }
 
 static inline int block_for(int64_t n) {
