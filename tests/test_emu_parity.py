@@ -99,3 +99,70 @@ def test_redundant_shape_updates_are_exact_noops():
         for col in FIELDS:
             x, y = a.get_state(col), b.get_state(col)
             assert np.array_equal(x, y, equal_nan=True), (t, col)
+
+
+@pytest.mark.parametrize("num_obstacles", [0, 1, 5, 8])
+def test_other_obstacle_counts(num_obstacles):
+    """Observation width 6 + 2 n, proximity penalty and collision over n obstacles (n = 0: no
+    obstacle term at all, salp_robot_env.py:373-383)."""
+    g = load_golden("ref_random.npz")
+    n, T = 24, 6
+    params = golden_params(g, precision=PRECISION_MIXED, num_obstacles=num_obstacles)
+    prod, orc = EmuBatch(n, params, seed=7), OracleVecEnv(n, params, seed=7)
+    assert prod.obs_dim == 6 + 2 * num_obstacles
+    acts = np.random.default_rng(3).uniform([0, 0, -1], [1, 1, 1], size=(T, n, 3)).astype(np.float32)
+    lockstep_compare(prod, orc, acts, resync=True, rtol=TOL_MIXED["rtol"], floor=TOL_MIXED["floor"],
+                     num_obstacles=num_obstacles)
+
+
+def test_non_default_robot_parameters():
+    """Nothing is hard-wired to make_env()'s literals: sea-water density, a heavier and longer body,
+    another nozzle, other penalties -- fp32 kernel body vs oracle, per-step tolerance."""
+    g = load_golden("ref_random.npz")
+    n, T = 48, 8
+    for prec, tol in ((PRECISION_F64, dict(rtol=1e-9, floor=1e-3)), (PRECISION_MIXED, dict(rtol=1e-5, floor=0.1))):
+        p = golden_params(g, precision=prec)
+        p.density = 1025.0
+        p.dry_mass = 1.3
+        p.init_length = 0.34
+        p.init_width = 0.16
+        p.nozzle_length1 = 0.04
+        p.nozzle_length2 = 0.06
+        p.nozzle_area = 0.0002
+        p.nozzle_mass = 0.8
+        p.discharge_coefficient = 0.35
+        p.drag_force_ratio = 0.2
+        p.added_mass_force[:] = [0.45, 0.65, 0.55]
+        p.added_mass_torque[:] = [0.25, 0.5, 0.7]
+        p.trans_drag_range[:] = [1.4, 2.6, 2.4, 1.6, 2.7, 1.3]
+        p.rot_drag_range[:] = [0.12, 0.28, 0.45, 0.25, 0.55, 0.15]
+        p.target_radius = 0.25
+        p.max_cycles = 40
+        prod, orc = EmuBatch(n, p, seed=11), OracleVecEnv(n, p, seed=11)
+        acts = np.random.default_rng(5).uniform([0.1, 0, -1], [1, 1, 1], size=(T, n, 3)).astype(np.float32)
+        report = {}
+        lockstep_compare(prod, orc, acts, resync=True, report=report, **tol)
+        print(prec, max(report.values()))
+
+
+def test_masked_reset_and_zero_substep_cycles():
+    g = load_golden("ref_random.npz")
+    n = 16
+    params = golden_params(g, precision=PRECISION_MIXED)
+    prod, orc = EmuBatch(n, params, seed=2), OracleVecEnv(n, params, seed=2)
+    prod.reset()
+    orc.reset()
+    a = np.tile(np.array([[0.5, 0.2, 0.3]], np.float32), (n, 1))
+    a[::2] = [0.0, 0.0, 0.0]              # K = 0 cycles: nothing moves, total < 0 (SURVEY 8c edge KAT)
+    for _ in range(3):
+        prod.step(a)
+        orc.step(a)
+        np.testing.assert_array_equal(prod.substeps, orc.substeps)
+        assert (prod.substeps[::2] == 0).all()
+    mask = np.zeros(n, np.uint8)
+    mask[[1, 4, 9]] = 1
+    o1, o2 = prod.reset(mask).copy(), orc.reset(mask).copy()
+    np.testing.assert_allclose(o1, o2, rtol=1e-6, atol=1e-6)
+    for col in ("episode_index", "cycle", "ep_length"):
+        np.testing.assert_array_equal(prod.get_state(col), orc.get_state(col))
+    assert (prod.get_state("cycle")[[1, 4, 9]] == 0).all() and (prod.get_state("cycle")[[0, 2, 3]] == 3).all()

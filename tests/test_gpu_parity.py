@@ -251,3 +251,24 @@ def test_pipeline_kernel_matches_fused_kernel():
             assert e.max() < 1e-5, (col, t, e.max())      # free-running: differences accumulate over the 12 steps
     print("pipeline vs fused: worst relative difference", worst)
     pipe.check()
+
+
+def test_other_obstacle_count_and_masked_device_reset():
+    import torch
+    g = load_golden("ref_random.npz")
+    n, T = 256, 6
+    params = golden_params(g, precision=PRECISION_MIXED, num_obstacles=5)
+    prod = SalpBatch(n, params, seed=7)
+    orc = OracleVecEnv(n, params, seed=7, threads=1)
+    assert prod.obs_dim == 16
+    acts = uniform_actions(np.random.default_rng(3), T, n)
+    lockstep_compare(prod, orc, acts, resync=True, rtol=TOL_MIXED["rtol"], floor=TOL_MIXED["floor"], num_obstacles=5)
+    mask = np.zeros(n, np.uint8)
+    mask[::7] = 1
+    obs_o = orc.reset(mask).copy()
+    prod.dev["obs"].copy_(torch.from_numpy(prod.obs).cuda())
+    obs_d = prod.reset_device(torch.from_numpy(mask).cuda())
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(obs_d.cpu().numpy()[mask == 1], obs_o[mask == 1], rtol=1e-6, atol=1e-6)
+    np.testing.assert_array_equal(prod.get_state("episode_index"), orc.get_state("episode_index"))
+    np.testing.assert_array_equal(prod.get_state("cycle"), orc.get_state("cycle"))
