@@ -155,6 +155,23 @@ class SalpBatch:
         v = np.ascontiguousarray(np.broadcast_to(values, (self.num_envs,)), field_dtype(name))
         self._check(self._L.salp_set_state(self._h, field_id(name), _np_ptr(v), 0, self.num_envs))
 
+    TRACE_COLUMNS = ("position_world", "euler_angle", "velocity", "angular_velocity", "length", "width")
+
+    def trace_cycle(self, env: int, action) -> dict:
+        """History feed: the per-substep histories the reference records with
+        Robot.enable_history_recording() (robot.py:681-776) for the NEXT cycle of one env, computed
+        in float64 reference arithmetic WITHOUT advancing the env.  Returns arrays of K rows."""
+        a = np.ascontiguousarray(action, np.float32).reshape(3)
+        cap = 4096
+        buf = np.zeros((cap, 14), np.float64)
+        K = C.c_int32(0)
+        self._check(self._L.salp_trace_cycle(self._h, int(env), _np_ptr(a), _np_ptr(buf), cap, C.byref(K)))
+        k = min(K.value, cap)
+        t = buf[:k]
+        return dict(substeps=K.value, position_world=t[:, 0:3].copy(), euler_angle=t[:, 3:6].copy(),
+                    velocity=t[:, 6:9].copy(), angular_velocity=t[:, 9:12].copy(), length=t[:, 12].copy(),
+                    width=t[:, 13].copy())
+
     # ------------------------------------------------------------------ device (torch) face
     def _device_buffers(self):
         if self._dev is None:

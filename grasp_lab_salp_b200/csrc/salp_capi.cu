@@ -404,6 +404,38 @@ int salp_state_ptr(salp_handle h, int32_t field, void** dev_ptr) {
   return SALP_OK;
 }
 
+int salp_trace_cycle(salp_handle h, int64_t env, const float* action_host, double* trace_host, int32_t capacity,
+                     int32_t* substeps_out) {
+  if (!h || !action_host || !trace_host || !substeps_out || capacity <= 0 || env < 0 || env >= h->view.n)
+    return SALP_ERR_INVALID;
+  DeviceGuard g(h->device);
+  if (capacity > SALP_MAX_SUBSTEPS) capacity = SALP_MAX_SUBSTEPS;
+  double* d_trace = nullptr;
+  int32_t* d_K = nullptr;
+  const size_t bytes = sizeof(double) * SALP_TRACE_WIDTH * (size_t)capacity;
+  CU(h, cudaMalloc((void**)&d_trace, bytes));
+  cudaError_t e = cudaMalloc((void**)&d_K, sizeof(int32_t));
+  int rc = SALP_OK;
+  if (e != cudaSuccess) rc = cuda_fail(h, e, "salp_trace_cycle: cudaMalloc");
+  if (rc == SALP_OK && salp_launch_trace(h->params, h->view, env, action_host, d_trace, capacity, d_K, h->host_stream) < 0)
+    rc = cuda_fail(h, cudaGetLastError(), "salp_trace_cycle launch");
+  int32_t K = 0;
+  if (rc == SALP_OK && (e = cudaMemcpyAsync(&K, d_K, sizeof K, cudaMemcpyDeviceToHost, h->host_stream)) != cudaSuccess)
+    rc = cuda_fail(h, e, "salp_trace_cycle: copy K");
+  if (rc == SALP_OK && (e = cudaStreamSynchronize(h->host_stream)) != cudaSuccess)
+    rc = cuda_fail(h, e, "salp_trace_cycle: kernel");
+  if (rc == SALP_OK) {
+    const int rows = K < capacity ? K : capacity;
+    if (rows > 0 && (e = cudaMemcpy(trace_host, d_trace, sizeof(double) * SALP_TRACE_WIDTH * rows, cudaMemcpyDeviceToHost)) != cudaSuccess)
+      rc = cuda_fail(h, e, "salp_trace_cycle: copy trace");
+    *substeps_out = K;
+    h->launches += 1;
+  }
+  cudaFree(d_trace);
+  if (d_K) cudaFree(d_K);
+  return rc;
+}
+
 int salp_check(salp_handle h) {
   if (!h) return SALP_ERR_INVALID;
   DeviceGuard g(h->device);

@@ -55,6 +55,8 @@ int salp_launch_reset(const SalpParams& p, const SalpView& v, const uint8_t* mas
 int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& io, uint32_t flags,
                      const SalpScratch& scratch, cudaStream_t stream);
 int salp_launch_init(const SalpParams& p, const SalpView& v, cudaStream_t stream);
+int salp_launch_trace(const SalpParams& p, const SalpView& v, int64_t env, const float action[3], double* trace,
+                      int capacity, int32_t* K_out, cudaStream_t stream);
 int salp_launch_ffma_probe(float* scratch, int blocks, int iters, cudaStream_t stream);
 
 // ---- rounding-exact scalar ops -------------------------------------------------------------

@@ -394,6 +394,31 @@ SALP_HD void env_step_end(const SalpParams& p, const SalpView& v, const SalpStep
   if ((flags & SALP_STEP_AUTORESET) && ended) env_reset(p, v, i, obs);
 }
 
+// History feed (salp_trace_cycle): the coming cycle of env i in float64 reference arithmetic on a
+// scratch copy of its state; one row per substep, taken after Robot.step() (robot.py:757-766).
+SALP_HD int env_trace_cycle(const SalpParams& p, const SalpView& v, int64_t i, float a0, float a1, float a2,
+                            double* trace, int capacity) {
+  Cols c{v, i};
+  CyclePlan plan = make_cycle_plan(p, a0, a1, a2, c.d(SALP_F_NOZZLE_ANGLE1), c.d(SALP_F_NOZZLE_ANGLE2));
+  Body64 b;
+  load_body(c, b);
+  refresh_shape_f64(p, b);
+  b.mass_rate = (b.water_mass - b.prev_volume * p.density) / p.dt;
+  double t = 0.0;
+  int K = 0;
+  while (cycle_running(plan, t) && K < SALP_MAX_SUBSTEPS) {
+    substep_f64(p, plan, b, t);
+    if (K < capacity) {
+      double* r = trace + (int64_t)SALP_TRACE_WIDTH * K;
+      for (int k = 0; k < 3; k++) { r[k] = b.pw[k]; r[3 + k] = b.eul[k]; r[6 + k] = b.v[k]; r[9 + k] = b.w[k]; }
+      r[12] = b.length;
+      r[13] = b.width;
+    }
+    K++;
+  }
+  return K;
+}
+
 template <int PREC>
 SALP_HD void env_step(const SalpParams& p, const SalpDerived& dv, const SalpView& v, const SalpStepIO& io,
                       uint32_t flags, int64_t i) {

@@ -20,6 +20,11 @@ __global__ void salp_reset_kernel(const __grid_constant__ SalpParams p, const __
   env_reset(p, v, i, obs ? obs + i * D : nullptr);
 }
 
+__global__ void salp_trace_kernel(const __grid_constant__ SalpParams p, const __grid_constant__ SalpView v, int64_t env,
+                                  float a0, float a1, float a2, double* trace, int capacity, int32_t* K_out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *K_out = env_trace_cycle(p, v, env, a0, a1, a2, trace, capacity);
+}
+
 // ---- K-sort: balance warps by substep count (SURVEY.md hard part 3) ----------------------------
 // salp_plan_kernel recomputes the cycle plan of every env (cheap: one inverse-kinematics solve)
 // and histograms the sort key (K bucket, end of shape motion); salp_scan_kernel turns the histogram into descending-K offsets;
@@ -92,6 +97,13 @@ int salp_launch_init(const SalpParams& p, const SalpView& v, cudaStream_t stream
 int salp_launch_reset(const SalpParams& p, const SalpView& v, const uint8_t* mask, float* obs,
                       cudaStream_t stream) {
   salp_reset_kernel<<<grid_for(v.n, 128), 128, 0, stream>>>(p, v, mask, obs);
+  SALP_LAUNCH_CHECK();
+  return 1;
+}
+
+int salp_launch_trace(const SalpParams& p, const SalpView& v, int64_t env, const float action[3], double* trace,
+                      int capacity, int32_t* K_out, cudaStream_t stream) {
+  salp_trace_kernel<<<1, 32, 0, stream>>>(p, v, env, action[0], action[1], action[2], trace, capacity, K_out);
   SALP_LAUNCH_CHECK();
   return 1;
 }

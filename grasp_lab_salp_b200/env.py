@@ -114,7 +114,7 @@ class SalpRobotEnv:
 
     def __init__(self, render_mode=None, width: int = 900, height: int = 700, robot: Robot | None = None,
                  num_obstacles: int = 2, obstacle_radius: float = 0.2, *, seed: int = 0, device: int = 0,
-                 precision=None, _cdll=None):
+                 precision=None, record: bool = False, _cdll=None):
         if render_mode is not None:
             raise NotImplementedError("rendering is out of scope of the GPU simulator (render_mode must be None)")
         self.render_mode = None
@@ -134,6 +134,14 @@ class SalpRobotEnv:
         self.action_space = spaces.action_space()
         self.observation_space = spaces.observation_space(num_obstacles)
         self.action = np.zeros(3)
+        self.record = bool(record)         # Robot.enable_history_recording(): per-substep histories in `info`
+        self.last_history = None
+
+    def enable_history_recording(self):
+        self.record = True
+
+    def disable_history_recording(self):
+        self.record = False
 
     # ---- gymnasium API ----
     def reset(self, seed=None, options=None):
@@ -146,8 +154,14 @@ class SalpRobotEnv:
         a = np.asarray(action, np.float32).reshape(1, 3)
         self.action = a[0]
         b = self._batch
+        hist = b.trace_cycle(0, a[0]) if self.record else None     # (does not advance the env)
+        self.last_history = hist
         obs, rew, term, trunc = b.step(a, auto_reset=False, extras=True)
-        info = {"position_history": [], "length_history": [], "width_history": []}
+        if hist is None:
+            info = {"position_history": [], "length_history": [], "width_history": []}
+        else:
+            info = {"position_history": hist["position_world"], "length_history": hist["length"],
+                    "width_history": hist["width"]}
         for j, k in enumerate(REWARD_TERM_NAMES):
             info[k] = float(b.terms[0, j])
         done, truncated = bool(term[0]), bool(trunc[0])

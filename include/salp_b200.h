@@ -236,6 +236,18 @@ int salp_set_state(salp_handle h, int32_t field, const void* host_src, int64_t f
 /* Raw device pointer of a column (zero-copy views for torch / cupy). */
 int salp_state_ptr(salp_handle h, int32_t field, void** dev_ptr);
 
+/* History feed -- replaces Robot.enable_history_recording() + the per-substep histories of
+ * Robot.step_through_cycle (robot.py:681-776) that SalpRobotEnv.step hands out as
+ * info["position_history" | "length_history" | "width_history"] (salp_robot_env.py:279-284) and the
+ * viewer / plotting tools read.  Runs the NEXT cycle of ONE env for `action_host[3]` in float64
+ * reference arithmetic on a scratch copy of its state (the env is NOT advanced) and writes one row
+ * per substep, taken after Robot.step() like the reference's histories:
+ *   row = [position_world xyz, euler_angle xyz, velocity xyz, angular_velocity xyz, length, width]
+ * trace_host: double[capacity][SALP_TRACE_WIDTH]; *substeps_out = K (rows beyond capacity are dropped). */
+#define SALP_TRACE_WIDTH 14
+int salp_trace_cycle(salp_handle h, int64_t env, const float* action_host, double* trace_host, int32_t capacity,
+                     int32_t* substeps_out);
+
 /* Sticky device-side status (e.g. SALP_ERR_RANGE); reading it synchronises the device. */
 int salp_check(salp_handle h);
 

@@ -121,6 +121,11 @@ int salp_set_state(salp_handle h, int32_t field, const void* src, int64_t first,
   memcpy(base + elem * first, src, elem * count);
   return SALP_OK;
 }
+int salp_trace_cycle(salp_handle h, int64_t env, const float* a, double* trace, int32_t capacity, int32_t* K_out) {
+  if (!h || !a || !trace || !K_out || env < 0 || env >= h->view.n) return SALP_ERR_INVALID;
+  *K_out = env_trace_cycle(h->params, h->view, env, a[0], a[1], a[2], trace, capacity);
+  return SALP_OK;
+}
 int salp_check(salp_handle h) { return h ? h->status : SALP_ERR_INVALID; }
 
 }  // extern "C"

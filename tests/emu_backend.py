@@ -12,7 +12,7 @@ from grasp_lab_salp_b200.batch import SalpBatch  # noqa: E402
 
 _EMU_SYMBOLS = {"salp_create", "salp_destroy", "salp_num_envs", "salp_obs_dim", "salp_last_error",
                 "salp_build_info", "salp_reset_host", "salp_step_host", "salp_set_scene_pool",
-                "salp_get_state", "salp_set_state", "salp_check", "salp_launch_count"}
+                "salp_get_state", "salp_set_state", "salp_check", "salp_launch_count", "salp_trace_cycle"}
 _cdll = None
 
 

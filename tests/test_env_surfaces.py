@@ -120,3 +120,38 @@ def test_single_env_replays_reference_trace_gpu():
 @pytest.mark.gpu
 def test_vec_env_has_sb3_semantics_gpu():
     _vec_env_has_sb3_semantics(_cdll(True), n=256, T=40)
+
+
+def _history_feed(cdll):
+    """record=True: info carries the per-substep histories of the cycle (robot.py:681-776); the
+    last row is the state the step leaves behind, the row count is K, and tracing does not
+    advance the env."""
+    g = load_golden("ref_fixed10.npz")
+    env = make_env(cdll)
+    env.enable_history_recording()
+    env.set_scene(g["targets"][0, 0], g["obstacles"][0, 0])
+    env.reset()
+    for t in range(4):
+        a = g["actions"][0, t]
+        before = env.robot.position_world.copy()
+        h = env._batch.trace_cycle(0, a)
+        np.testing.assert_array_equal(env.robot.position_world, before)          # not advanced
+        obs, rew, done, trunc, info = env.step(a)
+        K = int(g["K"][0, t])
+        assert h["substeps"] == K and info["position_history"].shape == (K, 3)
+        assert info["length_history"].shape == (K,) and info["width_history"].shape == (K,)
+        np.testing.assert_allclose(info["position_history"][-1], env.robot.position_world, rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(info["position_history"][-1][:2], g["state"][0, t, :2], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(env.last_history["euler_angle"][-1], env.robot.euler_angle, rtol=1e-12, atol=1e-15)
+        assert info["length_history"].min() >= 0.3 - 0.06 * a[0] - 1e-6 and abs(info["length_history"][-1] - 0.3) < 1e-12
+        np.testing.assert_allclose(info["length_history"] + info["width_history"], 0.45, rtol=1e-12)
+    env.close()
+
+
+def test_history_feed_emu():
+    _history_feed(_cdll(False))
+
+
+@pytest.mark.gpu
+def test_history_feed_gpu():
+    _history_feed(_cdll(True))
