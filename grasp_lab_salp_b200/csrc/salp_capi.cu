@@ -135,7 +135,7 @@ int salp_default_params(SalpParams* p) {
   p->max_cycles = 500;
   p->num_obstacles = 2;
   p->precision = SALP_PRECISION_MIXED;
-  p->reserved = 0;
+  p->randomization = 0;
   return SALP_OK;
 }
 
@@ -175,6 +175,9 @@ int salp_create(const SalpParams* params, int64_t num_envs, int device, uint64_t
   if (params->precision != SALP_PRECISION_F64 && params->precision != SALP_PRECISION_MIXED)
     return fail(nullptr, SALP_ERR_INVALID, "salp_create: unknown precision");
   if (!(params->dt > 0)) return fail(nullptr, SALP_ERR_INVALID, "salp_create: dt must be > 0");
+  if (params->randomization != 0 && params->precision != SALP_PRECISION_MIXED)
+    return fail(nullptr, SALP_ERR_INVALID, "salp_create: randomization needs SALP_PRECISION_MIXED "
+                                           "(the float64 reference mode is the deterministic restatement)");
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0 || device < 0 || device >= count)

@@ -61,6 +61,36 @@ SALP_DEV void sample_point(const SalpParams& p, uint64_t seed, int64_t gid, int 
   x = (float)rn::dadd(p.tank_x_min, rn::dmul(rn::dsub(p.tank_x_max, p.tank_x_min), u0));
   y = (float)rn::dadd(p.tank_y_min, rn::dmul(rn::dsub(p.tank_y_max, p.tank_y_min), u1));
 }
+// Randomisation streams (SalpParams.randomization): one Philox block per (global env id, episode,
+// cycle, purpose), keyed differently from the scene sampler.  u01: uniform in (0, 1).
+#define SALP_RNG_ACTION 1u
+#define SALP_RNG_OBS 2u          // .. 3
+#define SALP_RNG_DYNAMICS 4u     // .. 7
+#define SALP_RNG_OU 0x1000u      // + substep index
+SALP_DEV void rand_block(uint64_t seed, int64_t gid, uint32_t episode, uint32_t cycle, uint32_t purpose,
+                         uint32_t out[4]) {
+  out[0] = (uint32_t)gid;
+  out[1] = (uint32_t)((uint64_t)gid >> 32);
+  out[2] = episode;
+  out[3] = (cycle << 16) | purpose;
+  philox4x32_10(out, (uint32_t)seed ^ 0x5A17C0DEu, (uint32_t)(seed >> 32) ^ 0x9E3779B9u);
+}
+SALP_DEV float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+// randomize_scalar_jit (geometry.py:208-222): value * U(1 - u, 1 + u), clipped to [lo, hi]
+SALP_DEV float randomize_scalar(float value, float uncertainty, uint32_t bits, float lo, float hi) {
+  float s = value * (1.0f + uncertainty * (2.0f * u01(bits) - 1.0f));
+  return fminf(fmaxf(s, lo), hi);
+}
+
+// ... with the default (NaN) bounds: the clip is min(max(sample, v (1 - u)), v (1 + u)), which for a
+// NEGATIVE value has its bounds the wrong way round and always returns v (1 + u) -- a quirk of the
+// reference that e.g. observation randomisation inherits (verified on the live reference:
+// tests/golden/ref_randstats.npz, samples_observation, columns obs0 / obs4).
+SALP_DEV float randomize_scalar_default_bounds(float value, float uncertainty, uint32_t bits) {
+  if (value < 0.0f) return value * (1.0f + uncertainty);
+  return value * (1.0f + uncertainty * (2.0f * u01(bits) - 1.0f));
+}
+
 SALP_DEV float dist2f(float ax, float ay, float bx, float by) {  // float32 norm, no contraction
   float dx = rn::fsub(ax, bx), dy = rn::fsub(ay, by);
   return rn::fsqrt(rn::fadd(rn::fmul(dx, dx), rn::fmul(dy, dy)));
@@ -176,12 +206,17 @@ struct CyclePlan {
 SALP_DEV double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 SALP_DEV CyclePlan make_cycle_plan(const SalpParams& p, float a0, float a1, float a2,
-                                   double prev_angle1, double prev_angle2) {
+                                   double prev_angle1, double prev_angle2, const uint32_t* action_noise = nullptr) {
   CyclePlan c;
   // _rescale_action (salp_robot_env.py:166-174): float32 products under NEP 50
   c.contraction32 = rn::fmul(a0, (float)0.06);
   c.coast32 = rn::fmul(a1, (float)10.0);
   c.yaw32 = rn::fmul(a2, (float)(M_PI / 2));
+  if (action_noise) {   // _randomize_actions (salp_robot_env.py:176-181), on the rescaled action
+    c.contraction32 = randomize_scalar(c.contraction32, 0.1f, action_noise[0], 0.0f, 1.0f);
+    c.coast32 = randomize_scalar(c.coast32, 0.1f, action_noise[1], 0.0f, 20.0f);
+    c.yaw32 = randomize_scalar(c.yaw32, 0.1f, action_noise[2], -(float)(M_PI / 2), (float)(M_PI / 2));
+  }
   // Nozzle.solve_angles (robot.py:71-98)
   float s32, c32;
   np_sincosf(c.yaw32, s32, c32);

@@ -117,6 +117,9 @@ SALP_HD void env_reset(const SalpParams& p, const SalpView& v, int64_t i, float*
   // Robot.reset: motion state to zero; the nozzle (angle1, angle2, yaw) is NOT touched
   for (int f = SALP_F_VEL_X; f <= SALP_F_PREVANGLE_Z; f++) c.d(f) = 0.0;
   c.d(SALP_F_SPEED_WORLD) = 0.0;
+  c.d(SALP_F_OU_FORCE_X) = 0.0;        // force_disturbance.reset(), torque_disturbance.reset() (robot.py:454-455)
+  c.d(SALP_F_OU_FORCE_Y) = 0.0;
+  c.d(SALP_F_OU_TORQUE_Z) = 0.0;
   c.n(SALP_F_CYCLE) = 0;
   c.n(SALP_F_PHASE) = 3;
   // centre of mass is evaluated BEFORE length/width are restored (robot.py:478 vs :485-486)
@@ -241,6 +244,7 @@ struct StepCtx {
   double avg_vy, avg_wz;      // lag-by-one cycle averages (robot.py:744-745)
   double last_x, last_y;      // episode_positions[-1]
   int cycle;
+  RandCtx rc;                 // only meaningful when SalpParams.randomization != 0
 };
 
 SALP_HD void env_step_begin(const SalpParams& p, const SalpView& v, const SalpStepIO& io, int64_t i, StepCtx& cx,
@@ -250,8 +254,23 @@ SALP_HD void env_step_begin(const SalpParams& p, const SalpView& v, const SalpSt
   cx.a1 = io.actions[3 * i + 1];
   cx.a2 = io.actions[3 * i + 2];
   // :201-209  rescale, Nozzle.set_yaw_angle / solve_angles, Robot.set_control
-  cx.plan = make_cycle_plan(p, cx.a0, cx.a1, cx.a2, c.d(SALP_F_NOZZLE_ANGLE1), c.d(SALP_F_NOZZLE_ANGLE2));
   cx.cycle = c.n(SALP_F_CYCLE) + 1;
+  if (p.randomization) {
+    cx.rc.seed = v.seed;
+    cx.rc.gid = v.env_id_offset + i;
+    cx.rc.episode = (uint32_t)c.n(SALP_F_EPISODE_INDEX);
+    cx.rc.cycle = (uint32_t)cx.cycle;
+    cx.rc.ou_fx = (float)c.d(SALP_F_OU_FORCE_X);
+    cx.rc.ou_fy = (float)c.d(SALP_F_OU_FORCE_Y);
+    cx.rc.ou_tz = (float)c.d(SALP_F_OU_TORQUE_Z);
+  }
+  if (p.randomization & SALP_RAND_ACTION) {
+    uint32_t r[4];
+    rand_block(cx.rc.seed, cx.rc.gid, cx.rc.episode, cx.rc.cycle, SALP_RNG_ACTION, r);
+    cx.plan = make_cycle_plan(p, cx.a0, cx.a1, cx.a2, c.d(SALP_F_NOZZLE_ANGLE1), c.d(SALP_F_NOZZLE_ANGLE2), r);
+  } else {
+    cx.plan = make_cycle_plan(p, cx.a0, cx.a1, cx.a2, c.d(SALP_F_NOZZLE_ANGLE1), c.d(SALP_F_NOZZLE_ANGLE2));
+  }
   // :210  Robot.step_through_cycle (robot.py:740-757)
   load_body(c, b);
   const double tot = cx.plan.total64;
@@ -275,7 +294,14 @@ SALP_HD void env_step_end(const SalpParams& p, const SalpView& v, const SalpStep
   c.f(SALP_F_NOZZLE_YAW) = plan.yaw32;
   c.d(SALP_F_NOZZLE_ANGLE1) = plan.angle1;
   c.d(SALP_F_NOZZLE_ANGLE2) = plan.angle2;
-  c.n(SALP_F_CYCLE) = cycle;
+  // enable_latency (salp_robot_env.py:294-297): the extra set_control() after the step only bumps
+  // Robot.cycle (contraction 0, nothing is integrated) -- the timeout test below still sees `cycle`
+  c.n(SALP_F_CYCLE) = (p.randomization & SALP_RAND_LATENCY) ? cycle + 1 : cycle;
+  if (p.randomization & SALP_RAND_DISTURBANCE) {
+    c.d(SALP_F_OU_FORCE_X) = (double)cx.rc.ou_fx;
+    c.d(SALP_F_OU_FORCE_Y) = (double)cx.rc.ou_fy;
+    c.d(SALP_F_OU_TORQUE_Z) = (double)cx.rc.ou_tz;
+  }
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     c.d(SALP_F_PREVPOS_X + k) = pos0[k];
@@ -344,6 +370,13 @@ SALP_HD void env_step_end(const SalpParams& p, const SalpView& v, const SalpStep
   // :250  observation
   float* obs = io.obs + i * D;
   write_observation(p, c, b.pw, b.eul, b.v, b.w[2], obs);
+  if (p.randomization & SALP_RAND_OBSERVATION) {     // _randomize_observations (salp_robot_env.py:183-194)
+    uint32_t r[8];
+    rand_block(cx.rc.seed, cx.rc.gid, cx.rc.episode, cx.rc.cycle, SALP_RNG_OBS, r);
+    rand_block(cx.rc.seed, cx.rc.gid, cx.rc.episode, cx.rc.cycle, SALP_RNG_OBS + 1, r + 4);
+    const float unc[6] = {0.05f, 0.05f, 0.2f, 0.2f, 0.02f, 0.1f};
+    for (int k = 0; k < 6; k++) obs[k] = randomize_scalar_default_bounds(obs[k], unc[k], r[k]);
+  }
 
   // :258-276  termination (cumulative, not exclusive)
   bool done = false, trunc = false;
@@ -428,6 +461,6 @@ SALP_HD void env_step(const SalpParams& p, const SalpDerived& dv, const SalpView
   const double pos0[3] = {b.pos[0], b.pos[1], b.pos[2]};
   const double ang0[3] = {b.ang[0], b.ang[1], b.ang[2]};
   double t = 0.0;
-  const int K = run_cycle<PREC>(p, dv, cx.plan, v.time_table, b, t);
+  const int K = run_cycle<PREC>(p, dv, cx.plan, v.time_table, b, t, &cx.rc);
   env_step_end(p, v, io, flags, i, cx, pos0, ang0, b, K, t);
 }

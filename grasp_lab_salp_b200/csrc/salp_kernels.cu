@@ -125,7 +125,7 @@ int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& i
   const int block = block_for(v.n);
   // opt-in for small batches that fit one wave of 32-env blocks: the warp-specialised pipeline
   // (experimental: the fused latency kernel is currently faster, see profiles/README.md)
-  if (p.precision == SALP_PRECISION_MIXED && !order && (flags & SALP_STEP_PIPELINE) &&
+  if (p.precision == SALP_PRECISION_MIXED && p.randomization == 0 && !order && (flags & SALP_STEP_PIPELINE) &&
       v.n <= (int64_t)32 * (v.sm_count > 0 ? v.sm_count : 148)) {
     static bool configured = false;
     if (!configured) {
@@ -140,6 +140,8 @@ int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& i
   }
   if (p.precision == SALP_PRECISION_F64)
     salp_launch_step_f64(p, v, io, flags, order, stream);     // salp_step_f64.cu (compiled with -fmad=false)
+  else if (p.randomization != 0)       // default-off robustness switches: separate instantiation
+    salp_step_kernel<SALP_PRECISION_MIXED_RANDOMIZED><<<grid_for(v.n, block), block, 0, stream>>>(p, make_derived(p), v, io, flags, order);
   else if (block == 32)
     salp_step_kernel_lat<SALP_PRECISION_MIXED><<<grid_for(v.n, 32), 32, 0, stream>>>(p, make_derived(p), v, io, flags, order);
   else

@@ -156,15 +156,24 @@ SALP_DEV void substep_f64(const SalpParams& p, const CyclePlan& c, Body64& b, do
 // Robot.step_through_cycle's loop (robot.py:756-757).  Returns K, or -1 if the cycle would run
 // past SALP_MAX_SUBSTEPS (impossible for Box actions; guards against non-finite actions).
 struct SalpDerived;   // host-derived constants of the mixed loop (salp_loop_mixed.cuh); unused here
+// Per-env randomisation context of one cycle (SalpParams.randomization != 0, mixed loop only)
+struct RandCtx {
+  uint64_t seed;
+  int64_t gid;
+  uint32_t episode, cycle;
+  float ou_fx, ou_fy, ou_tz;      // OUDisturbance.state: force x, y and torque z (robot.py:279-280, 796-838)
+};
+#define SALP_PRECISION_MIXED_RANDOMIZED 2   // internal: MIXED with SalpParams.randomization != 0
 template <int PREC>
 SALP_HD int run_cycle(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c, const double* time_table,
-                      Body64& b, double& t);
+                      Body64& b, double& t, RandCtx* rc);
 
 template <>
 SALP_HD int run_cycle<SALP_PRECISION_F64>(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c,
-                                          const double* time_table, Body64& b, double& t) {
+                                          const double* time_table, Body64& b, double& t, RandCtx* rc) {
   (void)time_table;
   (void)dv;
+  (void)rc;
   refresh_shape_f64(p, b);
   b.mass_rate = (b.water_mass - b.prev_volume * p.density) / p.dt;
   t = 0.0;

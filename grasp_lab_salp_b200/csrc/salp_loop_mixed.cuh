@@ -163,6 +163,7 @@ struct Coef32 {
   float klI[3];       // (ratio -rho/2 Cr_i area_i width - I_rate_i) / I_i   (+ deform torque, :172-174)
   float JdI[3];       // (J_i2 - J_i1) / I_i
   float AdI[3];       // m (Ca_i2 - Ca_i1) / I_i
+  float inv_m, inv_Iz;  // only read by the disturbance variant (force / torque noise enter as F/m, T/I)
 };
 
 // fp64 side of the shape: the quantities that are differenced.
@@ -249,6 +250,8 @@ SALP_HD void make_coefs(const SalpDerived& k, const float dir[3], bool jet_on, f
     g.JdI[i] = (I[i2] * k.CatF[i2] - I[i1] * k.CatF[i1]) * inv_I[i];
     g.AdI[i] = m * k.CaD[i] * inv_I[i];
   }
+  g.inv_m = inv_m;
+  g.inv_Iz = inv_I1;
   g.tj1 = -armx * (dir[2] * f) * inv_I1;
   g.tj2 = armx * (dir[1] * f) * inv_I1;
   g.com = com;
@@ -272,7 +275,27 @@ struct Motion32 {
 
 // _newton_equations + _euler_equations + the velocity half of _update_motion_states
 // (robot.py:789-862) in the pre-divided form documented at Coef32.  ~80 FP32 instructions.
-SALP_HD void dyn_step(const SalpDerived& dv, const Coef32& g, Motion32& s) {
+// OUDisturbance.sample() for the three live components (robot.py:236-242): Euler-Maruyama step
+// x += theta (0 - x) dt + sigma sqrt(dt) N(0, 1), theta = 2, sigma = 0.05 (force) / 0.01 (torque)
+SALP_HD void ou_step(const SalpDerived& dv, RandCtx& rc, int k) {
+  uint32_t r[4];
+  rand_block(rc.seed, rc.gid, rc.episode, rc.cycle, SALP_RNG_OU + (uint32_t)k, r);
+  const float two_pi = 6.2831853f;
+#ifdef __CUDA_ARCH__
+  float m0 = sqrtf(-2.0f * __logf(u01(r[0]))), m1 = sqrtf(-2.0f * __logf(u01(r[2])));
+  float n0 = m0 * __cosf(two_pi * u01(r[1])), n1 = m0 * __sinf(two_pi * u01(r[1])), n2 = m1 * __cosf(two_pi * u01(r[3]));
+#else
+  float m0 = sqrtf(-2.0f * logf(u01(r[0]))), m1 = sqrtf(-2.0f * logf(u01(r[2])));
+  float n0 = m0 * cosf(two_pi * u01(r[1])), n1 = m0 * sinf(two_pi * u01(r[1])), n2 = m1 * cosf(two_pi * u01(r[3]));
+#endif
+  const float decay = 1.0f - 2.0f * dv.dt, sq = sqrtf(dv.dt);
+  rc.ou_fx = rc.ou_fx * decay + 0.05f * sq * n0;
+  rc.ou_fy = rc.ou_fy * decay + 0.05f * sq * n1;
+  rc.ou_tz = rc.ou_tz * decay + 0.01f * sq * n2;
+}
+
+template <bool NOISE = false>
+SALP_HD void dyn_step(const SalpDerived& dv, const Coef32& g, Motion32& s, RandCtx* rc = nullptr, int k = 0) {
   const float v0 = s.v0, v1 = s.v1, v2 = s.v2, w0 = s.w0, w1 = s.w1, w2 = s.w2;
   float sd = fast_norm3(v0, v1, v2) + dv.ratio_f;               // |v| v + ratio v = v (|v| + ratio)
   float wn = fast_norm3(w0, w1, w2);
@@ -287,6 +310,12 @@ SALP_HD void dyn_step(const SalpDerived& dv, const Coef32& g, Motion32& s) {
   float nl0 = w0 * fmaf(g.kqI[0], wn, g.klI[0]) - dv.Cat[0] * s.al0 - (w1 * w2) * g.JdI[0] - (v1 * v2) * g.AdI[0];
   float nl1 = g.tj1 + w1 * fmaf(g.kqI[1], wn, g.klI[1]) - dv.Cat[1] * s.al1 - (w2 * w0) * g.JdI[1] - (v2 * v0) * g.AdI[1];
   float nl2 = g.tj2 + w2 * fmaf(g.kqI[2], wn, g.klI[2]) - dv.Cat[2] * s.al2 - (w0 * w1) * g.JdI[2] - (v0 * v1) * g.AdI[2];
+  if (NOISE) {        // force_noise / torque_noise join the sums of _newton_equations / _euler_equations
+    ou_step(dv, *rc, k);
+    na0 = fmaf(rc->ou_fx, g.inv_m, na0);
+    na1 = fmaf(rc->ou_fy, g.inv_m, na1);
+    nl2 = fmaf(rc->ou_tz, g.inv_Iz, nl2);
+  }
   s.ac0 = na0; s.ac1 = na1; s.ac2 = na2;
   s.al0 = nl0; s.al1 = nl1; s.al2 = nl2;
   s.v0 = fmaf(na0, dv.dt, v0); s.v1 = fmaf(na1, dv.dt, v1); s.v2 = fmaf(na2, dv.dt, v2);
@@ -473,9 +502,9 @@ SALP_HD int next_update_after(int j, const PhasePlan& pp) {
          : (j < pp.upd_b_begin ? pp.upd_b_begin : 0x7fffffff);
 }
 
-template <>
-SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c,
-                                            const double* time_table, Body64& b, double& t_out) {
+template <bool NOISE>
+SALP_HD int run_cycle_mixed(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c, const double* time_table,
+                            Body64& b, double& t_out, RandCtx* rc) {
   // ---- K: first k with !(t_k < total) in the dtype the reference compares in (robot.py:756) ----
   const int K = plan_substeps(c, time_table);
   t_out = 0.0;
@@ -503,7 +532,7 @@ SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDeriv
   // lean body.  With the K-sort's second key (end of shape motion) W is close to every lane's own end.
   const int lane_end = pp.upd_a_end > pp.upd_b_end ? pp.upd_a_end : pp.upd_b_end;
   const int W = warp_max_int(lane_end < K ? lane_end : K);
-  dyn_step(dv, g, s);
+  dyn_step<NOISE>(dv, g, s, rc, 0);
   shape_update(p, dv, c, time_table, dir, 1, pp.k_T0, pp.k_jet, st, g);
 
   int k = 1;
@@ -517,12 +546,12 @@ SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDeriv
     const int aend = kA < cend ? kA : cend;
     for (; k < aend; k++) {
       kin_step(dv, s);
-      dyn_step(dv, g, s);
+      dyn_step<NOISE>(dv, g, s, rc, k);
       shape_update(p, dv, c, time_table, dir, k + 1, pp.k_T0, pp.k_jet, st, g);
     }
     for (; k < cend; k++) {
       kin_step(dv, s);
-      dyn_step(dv, g, s);
+      dyn_step<NOISE>(dv, g, s, rc, k);
     }
     if (k == boundary) flush_chunk(b, s);       // two-level sums (fp32 chunk partials -> fp64 totals)
   }
@@ -538,4 +567,50 @@ SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDeriv
   b.speed_world = (double)sqrtf(s.vw0 * s.vw0 + s.vw1 * s.vw1);
   t_out = tK;
   return K;
+}
+
+template <>
+SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c,
+                                            const double* time_table, Body64& b, double& t_out, RandCtx* rc) {
+  (void)rc;
+  return run_cycle_mixed<false>(p, dv, c, time_table, b, t_out, nullptr);
+}
+
+// SalpParams.randomization != 0: per-env coefficient draws (Robot._randomize_parameters,
+// robot.py:594-628: discharge coefficient, the two drag ratios and the added-mass diagonals, each
+// mean * U(0.5, 1.5), re-drawn every cycle) replace the launch-wide constants in a thread-local copy
+// of SalpDerived; OU disturbances run inside dyn_step.
+SALP_HD void randomize_derived(const SalpParams& p, uint32_t flags, const RandCtx& rc, SalpDerived& k) {
+  if (!(flags & SALP_RAND_DYNAMICS)) return;
+  uint32_t r[16];
+  for (uint32_t q = 0; q < 4; q++) rand_block(rc.seed, rc.gid, rc.episode, rc.cycle, SALP_RNG_DYNAMICS + q, r + 4 * q);
+  const float cd = randomize_scalar((float)p.discharge_coefficient, 0.5f, r[0], 0.0f, 1.0f);
+  k.ratio_f = randomize_scalar_default_bounds((float)p.drag_force_ratio, 0.5f, r[1]);
+  k.torque_ratio = randomize_scalar_default_bounds((float)p.drag_torque_ratio, 0.5f, r[2]);
+  k.jet_gain_f = (float)(-(double)cd * p.density / p.nozzle_area);
+  k.jet_gain = (double)k.jet_gain_f;
+  float ca[3], cat[3];
+  for (int i = 0; i < 3; i++) {
+    ca[i] = randomize_scalar((float)p.added_mass_force[i], 0.5f, r[3 + i], -1e30f, 1e30f);
+    k.Car[i] = randomize_scalar((float)p.added_mass_rate_force[i], 0.5f, r[6 + i], -1e30f, 1e30f);
+    cat[i] = randomize_scalar((float)p.added_mass_torque[i], 0.5f, r[9 + i], -1e30f, 1e30f);
+  }
+  for (int i = 0; i < 3; i++) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+    k.Ca[i] = ca[i];
+    k.E[i] = 1.0f + ca[i];
+    k.Cat[i] = cat[i];
+    k.CaD[i] = ca[i2] - ca[i1];
+    k.CatF[i] = 1.0f + cat[i];
+  }
+}
+
+template <>
+SALP_HD int run_cycle<SALP_PRECISION_MIXED_RANDOMIZED>(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c,
+                                                       const double* time_table, Body64& b, double& t_out,
+                                                       RandCtx* rc) {
+  SalpDerived k = dv;
+  randomize_derived(p, (uint32_t)p.randomization, *rc, k);
+  if (p.randomization & SALP_RAND_DISTURBANCE) return run_cycle_mixed<true>(p, k, c, time_table, b, t_out, rc);
+  return run_cycle_mixed<false>(p, k, c, time_table, b, t_out, rc);
 }

@@ -23,6 +23,8 @@ STEP_AUTORESET = 1
 STEP_SORT_BY_K = 2
 STEP_PIPELINE = 4
 
+RAND_ACTION, RAND_OBSERVATION, RAND_DYNAMICS, RAND_DISTURBANCE, RAND_LATENCY = 1, 2, 4, 8, 16
+
 REWARD_TERM_NAMES = ("rewards/track", "rewards/heading", "rewards/smooth", "rewards/yaw",
                      "rewards/time", "rewards/sideslip", "rewards/obstacle")
 
@@ -57,7 +59,7 @@ class SalpParams(C.Structure):
         ("success_bonus", C.c_double), ("out_of_bounds_penalty", C.c_double),
         ("collision_penalty", C.c_double), ("timeout_penalty", C.c_double),
         ("max_cycles", C.c_int32), ("num_obstacles", C.c_int32),
-        ("precision", C.c_int32), ("reserved", C.c_int32),
+        ("precision", C.c_int32), ("randomization", C.c_int32),
     ]
 
     def copy(self) -> "SalpParams":
@@ -82,7 +84,7 @@ def fit_timing_polynomials():
 
 def default_params(*, precision: int = PRECISION_MIXED, num_obstacles: int = 2,
                    obstacle_radius: float = 0.2, width: int = 900, height: int = 700,
-                   refill_poly=None, jet_poly=None) -> SalpParams:
+                   refill_poly=None, jet_poly=None, randomization: int = 0) -> SalpParams:
     if not 0 <= num_obstacles <= MAX_OBSTACLES:
         raise ValueError(f"num_obstacles must be in [0, {MAX_OBSTACLES}]")
     p = SalpParams()
@@ -134,7 +136,7 @@ def default_params(*, precision: int = PRECISION_MIXED, num_obstacles: int = 2,
     p.max_cycles = 500
     p.num_obstacles = num_obstacles
     p.precision = precision
-    p.reserved = 0
+    p.randomization = int(randomization)
     return p
 
 
@@ -148,7 +150,7 @@ _F64_NAMES = (
     "nozzle_angle1 nozzle_angle2 prev_dist speed_world "
     "ep_return ep_path_length ep_initial_distance ep_sum_a0 ep_sum_a1 ep_sum_abs_a2 ep_sum_speed "
     "ep_sum_term0 ep_sum_term1 ep_sum_term2 ep_sum_term3 ep_sum_term4 ep_sum_term5 ep_sum_term6 "
-    "ep_substeps").split()
+    "ep_substeps ou_force_x ou_force_y ou_torque_z").split()
 F32_BASE = 1000
 I32_BASE = 2000
 _F32_NAMES = ["nozzle_yaw", "prev_action0", "prev_action1", "prev_action2", "target_x", "target_y"]

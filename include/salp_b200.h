@@ -54,6 +54,15 @@ typedef enum SalpPrecision {
   SALP_PRECISION_MIXED = 1    /* fp32 motion state, fp64 finite-difference core + accumulators */
 } SalpPrecision;
 
+/* SalpParams.randomization: the reference's default-off robustness switches, sampled on the device
+ * from counter-based Philox streams keyed by (seed, global env id, episode, cycle): statistical,
+ * not bitwise, parity with the reference's global np.random draws.  SALP_PRECISION_MIXED only. */
+#define SALP_RAND_ACTION 1u        /* SalpRobotEnv.enable_action_randomization, salp_robot_env.py:176-181: +-10 % */
+#define SALP_RAND_OBSERVATION 2u   /* enable_observation_randomization, :183-194 */
+#define SALP_RAND_DYNAMICS 4u      /* Robot.enable_dynamic_randomization, robot.py:594-628: 7 coefficient groups +-50 % per cycle */
+#define SALP_RAND_DISTURBANCE 8u   /* Robot.enable_disturbances, robot.py:210-242, 796-838: OU force (x, y) / torque (z) noise */
+#define SALP_RAND_LATENCY 16u      /* enable_latency, salp_robot_env.py:294-297: the extra set_control (cycle += 1) */
+
 /* salp_step flags */
 #define SALP_STEP_AUTORESET 1u     /* SB3 VecEnv semantics: reset finished envs, obs = post-reset obs */
 #define SALP_STEP_SORT_BY_K 2u     /* balance warps: order envs by substep count before the loop */
@@ -90,7 +99,7 @@ typedef struct SalpParams {
   int32_t max_cycles;                 /* salp_robot_env.py:274 */
   int32_t num_obstacles;              /* <= SALP_MAX_OBSTACLES */
   int32_t precision;                  /* SalpPrecision */
-  int32_t reserved;
+  int32_t randomization;              /* SALP_RAND_* bits; 0 = the reference's defaults (everything off) */
 } SalpParams;
 
 typedef struct SalpSim* salp_handle;
@@ -156,6 +165,7 @@ typedef enum SalpField {
   SALP_F_EP_SUM_TERM0, SALP_F_EP_SUM_TERM1, SALP_F_EP_SUM_TERM2, SALP_F_EP_SUM_TERM3,
   SALP_F_EP_SUM_TERM4, SALP_F_EP_SUM_TERM5, SALP_F_EP_SUM_TERM6,
   SALP_F_EP_SUBSTEPS,
+  SALP_F_OU_FORCE_X, SALP_F_OU_FORCE_Y, SALP_F_OU_TORQUE_Z,     /* OUDisturbance.state (robot.py:279-280), SALP_RAND_DISTURBANCE */
   SALP_NUM_F64_FIELDS,
 
   /* F32 columns */

@@ -81,6 +81,8 @@ int salp_step_host(salp_handle h, const SalpStepIO* io, uint32_t flags) {
   for (int64_t i = 0; i < h->view.n; i++) {
     if (h->params.precision == SALP_PRECISION_F64)
       env_step<SALP_PRECISION_F64>(h->params, dv, h->view, *io, flags, i);
+    else if (h->params.randomization != 0)
+      env_step<SALP_PRECISION_MIXED_RANDOMIZED>(h->params, dv, h->view, *io, flags, i);
     else
       env_step<SALP_PRECISION_MIXED>(h->params, dv, h->view, *io, flags, i);
   }

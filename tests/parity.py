@@ -167,7 +167,7 @@ def all_columns():
     global ALL_COLUMNS
     if ALL_COLUMNS is None:
         from grasp_lab_salp_b200.params import FIELDS
-        ALL_COLUMNS = [n for n in FIELDS if n != "speed_world"] + ["speed_world"]
+        ALL_COLUMNS = [n for n in FIELDS if n != "speed_world" and not n.startswith("ou_")] + ["speed_world"]
     return ALL_COLUMNS
 
 

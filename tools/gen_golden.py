@@ -144,6 +144,33 @@ def run_blowup_case(args):
     return raised, counter["k"], np.array([*r.position_world[:2], r.euler_angle[2]], np.float64)
 
 
+RAND_ACTIONS = np.array([[0.6, 0.2, 0.3], [0.5, 0.3, -0.4], [0.7, 0.1, 0.2]], np.float32)
+
+
+def run_rand_case(args):
+    """3 fixed cycles from rest with ONE of the reference's robustness switches on; global
+    np.random seeded per sample.  Returns final (x, y, yaw, vx, vy, wz), last obs[:6], yaw command."""
+    mode, seed = args
+    np.random.seed(seed)
+    env = rh.make_env()
+    if mode == "dynamics":
+        env.robot.enable_dynamic_randomization()
+    elif mode == "disturbance":
+        env.robot.enable_disturbances()
+    elif mode == "action":
+        env.enable_action_randomization()
+    elif mode == "observation":
+        env.enable_observation_randomization()
+    env.reset()
+    rh.inject_scene(env, [1.8, 1.2], [[-1.5, -1.0], [1.5, -1.0]])
+    obs = None
+    for a in RAND_ACTIONS:
+        obs, rew, done, trunc, info = env.step(a.copy())
+    r = env.robot
+    return np.array([r.position_world[0], r.position_world[1], r.euler_angle[2], r.velocity[0], r.velocity[1],
+                     r.angular_velocity[2], *obs[:6], float(r.nozzle.yaw)], np.float64)
+
+
 def gather(results):
     keys = results[0].keys()
     return {k: np.stack([r[k] for r in results]) for k in keys}
@@ -168,7 +195,7 @@ def write(name, actions, targets, obstacles, note):
 
 def main():
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
-    which = sys.argv[1:] or ["fixed10", "edge", "random", "clipped", "blowup"]
+    which = sys.argv[1:] or ["fixed10", "edge", "random", "clipped", "blowup", "randstats"]
     rng = np.random.default_rng(20261018)
 
     if "fixed10" in which:
@@ -227,6 +254,25 @@ def main():
             jet_poly=m.geometry.fit_compression_propulsion_time_relation_jit(),
             note=np.array("one cycle from rest, carried nozzle angles injected; raised = reference threw LinAlgError"))
         print(f"ref_blowup.npz: {n} cases, reference raised in {sum(r[0] for r in res)}")
+
+
+    if "randstats" in which:
+        # distributions of the outcome of 3 fixed cycles under each default-off robustness switch
+        n = 320
+        out = {}
+        with Pool(8) as pool:
+            for mode in ("none", "dynamics", "disturbance", "action", "observation"):
+                res = pool.map(run_rand_case, [(mode, 1000 + i) for i in range(n if mode != "none" else 1)])
+                out[mode] = np.stack(res)
+                print(mode, "mean", out[mode].mean(0)[:6], "std", out[mode].std(0)[:6])
+        m = rh.load()
+        np.savez_compressed(
+            os.path.join(ROOT, "tests", "golden", "ref_randstats.npz"), actions=RAND_ACTIONS,
+            columns=np.array(["x", "y", "yaw", "vx", "vy", "wz", "obs0", "obs1", "obs2", "obs3", "obs4", "obs5", "nozzle_yaw"]),
+            refill_poly=m.geometry.fit_compression_refill_time_relation_jit(),
+            jet_poly=m.geometry.fit_compression_propulsion_time_relation_jit(),
+            note=np.array("3 fixed cycles from rest, scene target (1.8,1.2); one robustness switch per set; 320 samples each"),
+            **{f"samples_{k}": v for k, v in out.items()})
 
 
 if __name__ == "__main__":
