@@ -332,9 +332,12 @@ SALP_HD void dyn_step(const SalpDerived& dv, const Coef32& g, Motion32& s, RandC
 // the increment is clamped so that the pair stays a unit vector, and the true angle -- which keeps
 // accumulating the unclamped increment -- re-anchors it at the next flush.
 SALP_HD void rotate_small(float d, float& sn, float& cs) {
-  d = fminf(fmaxf(d, -0.55f), 0.55f);
-  float sd_, cd_;
-  sincos_small(d, sd_, cd_);
+  // per-substep increments are ~1e-2 rad: sin d = d - d^3/6 + d^5/120, cos d = 1 - d^2/2 + d^4/24
+  // (truncation < 1e-10 there, 2e-7 at the clamp)
+  d = fminf(fmaxf(d, -0.25f), 0.25f);
+  const float d2 = d * d;
+  const float sd_ = d * fmaf(d2, fmaf(d2, 8.3333333e-3f, -1.6666667e-1f), 1.0f);
+  const float cd_ = fmaf(d2, fmaf(d2, 4.1666667e-2f, -0.5f), 1.0f);
   float ns = sn * cd_ + cs * sd_;
   cs = cs * cd_ - sn * sd_;
   sn = ns;
@@ -399,9 +402,15 @@ struct ShapeTrack {
 
 // update_state + update_properties after substep j-1 (robot.py:640-668), only called while the
 // shape moves or its backward differences have not been flushed yet.
+SALP_HD void shape_update_at(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c, double t,
+                             const float dir[3], int j, int k_T0, int k_jet, ShapeTrack& st, Coef32& g);
 SALP_HD void shape_update(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c, const double* time_table,
                           const float dir[3], int j, int k_T0, int k_jet, ShapeTrack& st, Coef32& g) {
-  const double t = time_table[j];
+  shape_update_at(p, dv, c, time_table[j], dir, j, k_T0, k_jet, st, g);
+}
+// t = t_j, the j-fold repeated `cycle_time += dt` (callers either read the table or carry the sum)
+SALP_HD void shape_update_at(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c, double t,
+                             const float dir[3], int j, int k_T0, int k_jet, ShapeTrack& st, Coef32& g) {
   const int phase = j < k_T0 ? 0 : (j < k_jet ? 1 : 2);
   st.dl = shape_delta(phase, t, c.refill, c.T0, (double)c.contraction32, c.contract_rate, c.release_rate);
   double lh = 0.5 * (p.init_length - st.dl), wh = 0.5 * (p.init_width + st.dl);
@@ -537,6 +546,7 @@ SALP_HD int run_cycle_mixed(const SalpParams& p, const SalpDerived& dv, const Cy
 
   int k = 1;
   const int kA = W < K ? W : K;                  // part A covers updates j = k + 1 <= W
+  double tj = time_table[1];                     // carried through part A by the same additions as the table
   // Chunk boundaries are FIXED (after iterations 16, 32, ...: kinematic updates 0..15, 16..31, ...)
   // so that the grouping of the fp32 chunk sums -- hence every bit of the result -- does not
   // depend on W, i.e. on which envs share the warp.
@@ -547,7 +557,8 @@ SALP_HD int run_cycle_mixed(const SalpParams& p, const SalpDerived& dv, const Cy
     for (; k < aend; k++) {
       kin_step(dv, s);
       dyn_step<NOISE>(dv, g, s, rc, k);
-      shape_update(p, dv, c, time_table, dir, k + 1, pp.k_T0, pp.k_jet, st, g);
+      tj = rn::dadd(tj, p.dt);
+      shape_update_at(p, dv, c, tj, dir, k + 1, pp.k_T0, pp.k_jet, st, g);
     }
     for (; k < cend; k++) {
       kin_step(dv, s);
