@@ -160,9 +160,12 @@ SALP_DEV T drag_interp_weight(const SalpParams& p, T length, T width) {
 // geometry.py:40-50 and :54-64; `dl` is what is subtracted from init_length / added to init_width
 SALP_DEV double shape_delta(int phase, double t, double refill, double T0, double contraction,
                             double contract_rate, double release_rate) {
-  if (phase == 0) return (t < refill) ? t * contract_rate : contraction;
-  if (phase == 1) return contraction - (t - T0) * release_rate;
-  return 0.0;
+  // branch-free on purpose (selects): inside the substep loop a branch here would split the basic
+  // block and keep the scheduler from overlapping the fp64 shape chain with the fp32 chains
+  const double refill_dl = (t < refill) ? t * contract_rate : contraction;
+  const double jet_dl = contraction - (t - T0) * release_rate;
+  const double d = (phase == 1) ? jet_dl : 0.0;
+  return (phase == 0) ? refill_dl : d;
 }
 
 // --------------------------------------------------------------------------------------------
