@@ -333,10 +333,14 @@ SALP_HD void env_step_end(const SalpParams& p, const SalpView& v, const SalpStep
   double terms[7];
   terms[0] = (-dist + c.d(SALP_F_PREV_DIST)) * 100;
   c.d(SALP_F_PREV_DIST) = dist;
+  // The body-frame vector of the reward (pos - target, :357-359) is the exact negative of the one in
+  // the observation (target - pos, :653-656), and r_heading takes atan2 of ITS negative: both use
+  // the same atan2(by, bx) of the body-frame target vector.  One rotation, one atan2.
   Rot3 R = rotation_zyx(b.eul[0], b.eul[1], b.eul[2]);
   double bx, by;
-  to_body_frame_xy(R, dx, dy, bx, by);
-  terms[1] = -0.5 * fabs(atan2(-by, -bx));
+  to_body_frame_xy(R, -dx, -dy, bx, by);
+  const double heading = atan2(by, bx);
+  terms[1] = -0.5 * fabs(heading);
   const int ep_len = c.n(SALP_F_EP_LENGTH);
   if (ep_len == 0) {
     // first step of an episode: prev_action is reset()'s float64 zeros (:128) -> float64 arithmetic
@@ -369,7 +373,16 @@ SALP_HD void env_step_end(const SalpParams& p, const SalpView& v, const SalpStep
 
   // :250  observation
   float* obs = io.obs + i * D;
-  write_observation(p, c, b.pw, b.eul, b.v, b.w[2], obs);
+  obs[0] = (float)bx;                                   // _get_observation (:651-670), sharing R and the heading
+  obs[1] = (float)by;
+  obs[2] = (float)b.v[0];
+  obs[3] = (float)b.v[1];
+  obs[4] = (float)b.w[2];
+  obs[5] = (float)heading;
+  for (int k = 0; k < p.num_obstacles; k++) {
+    obs[6 + 2 * k] = (float)((double)c.f(SALP_F_OBSTACLE0_X + 2 * k) - b.pw[0]);
+    obs[7 + 2 * k] = (float)((double)c.f(SALP_F_OBSTACLE0_X + 2 * k + 1) - b.pw[1]);
+  }
   if (p.randomization & SALP_RAND_OBSERVATION) {     // _randomize_observations (salp_robot_env.py:183-194)
     uint32_t r[8];
     rand_block(cx.rc.seed, cx.rc.gid, cx.rc.episode, cx.rc.cycle, SALP_RNG_OBS, r);

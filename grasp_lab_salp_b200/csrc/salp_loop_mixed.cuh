@@ -25,7 +25,7 @@
 #pragma once
 #include "salp_loop_f64.cuh"
 
-#define SALP_MIXED_CHUNK 16
+#define SALP_MIXED_CHUNK 32
 
 // ---- MUFU-based reciprocal / norm with one Newton step (~1 ulp, no slow-path branches) --------
 SALP_HD float fast_rcp(float x) {
