@@ -24,7 +24,7 @@
 #pragma once
 #include "salp_env.cuh"
 
-#define SALP_PIPE_CHUNK 32
+#define SALP_PIPE_CHUNK 16
 #define SALP_PIPE_SLOTS (2 * SALP_PIPE_CHUNK)
 #define SALP_PIPE_NCOEF 26
 #define SALP_PIPE_THREADS 96
