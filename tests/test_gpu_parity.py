@@ -239,7 +239,7 @@ def test_pipeline_kernel_matches_fused_kernel():
         np.testing.assert_array_equal(tr1, tr2)
         for col in ("cycle", "phase", "ep_length", "episode_index"):
             np.testing.assert_array_equal(pipe.get_state(col), fused.get_state(col))
-        np.testing.assert_allclose(o1, o2, rtol=2e-6, atol=2e-6)
+        np.testing.assert_allclose(o1, o2, rtol=1e-5, atol=1e-5)       # (chunk grouping differs: 16 vs 32 substeps)
         np.testing.assert_allclose(r1, r2, rtol=1e-5, atol=2e-4)
         for col in ("posw_x", "posw_y", "vel_x", "vel_y", "euler_z", "angvel_z", "length", "width", "prev_volume",
                     "com_x", "com_rate_x", "com_acc_x", "prev_i_y", "pos_x", "angle_z", "acc_x", "angacc_z"):
