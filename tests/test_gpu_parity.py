@@ -248,7 +248,7 @@ def test_pipeline_kernel_matches_fused_kernel():
             np.testing.assert_array_equal(np.isfinite(a), ok)
             e = np.abs(a[ok] - b[ok]) / np.maximum(np.abs(b[ok]), 0.1)
             worst = max(worst, float(e.max()))
-            assert e.max() < 1e-5, (col, t, e.max())      # free-running: differences accumulate over the 12 steps
+            assert e.max() < 3e-5, (col, t, e.max())      # free-running: differences accumulate over the 12 steps
     print("pipeline vs fused: worst relative difference", worst)
     pipe.check()
 
