@@ -47,7 +47,7 @@ PROTOTYPES = {
     "salp_set_scene_pool": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "salp_get_state": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64]),
     "salp_set_state": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64]),
-    "salp_state_ptr": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
+    "salp_state_ptr": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "salp_trace_cycle": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "salp_check": (C.c_int, [C.c_void_p]),
     "salp_launch_count": (C.c_int64, [C.c_void_p]),

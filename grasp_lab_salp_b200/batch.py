@@ -242,13 +242,14 @@ class SalpBatch:
         return self._device_buffers()
 
     def state_tensor(self, name: str):
-        """Zero-copy torch view of one state column (salp_state_ptr)."""
+        """Zero-copy (strided) torch view of one state field over all envs (salp_state_ptr)."""
         import torch
         p = C.c_void_p()
-        self._check(self._L.salp_state_ptr(self._h, field_id(name), C.byref(p)))
+        stride = C.c_int64(0)
+        self._check(self._L.salp_state_ptr(self._h, field_id(name), C.byref(p), C.byref(stride)))
         dt = {np.float64: torch.float64, np.float32: torch.float32, np.int32: torch.int32}[field_dtype(name)]
         iface = {"shape": (self.num_envs,), "typestr": np.dtype(field_dtype(name)).str,
-                 "data": (p.value, False), "version": 2}
+                 "data": (p.value, False), "version": 2, "strides": (int(stride.value),)}
 
         class _Holder:
             __cuda_array_interface__ = iface

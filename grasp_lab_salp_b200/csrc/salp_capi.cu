@@ -362,48 +362,61 @@ int salp_set_scene_pool(salp_handle h, const float* targets_host, const float* o
   return SALP_OK;
 }
 
-static int column_of(SalpSim* h, int32_t field, char** base, size_t* elem) {
+// address of env 0's element of `field`, element size and byte stride between consecutive envs
+static int column_of(SalpSim* h, int32_t field, char** base, size_t* elem, size_t* stride) {
   const int64_t n = h->view.n;
+  int64_t local, nfields;
+  char* arr;
   if (field >= 0 && field < SALP_NUM_F64_FIELDS) {
-    *base = (char*)(h->view.f64 + (int64_t)field * n); *elem = sizeof(double); return SALP_OK;
+    local = field; nfields = SALP_NUM_F64_FIELDS; arr = (char*)h->view.f64; *elem = sizeof(double);
+  } else if (field >= SALP_F32_BASE && field < SALP_F32_END) {
+    local = field - SALP_F32_BASE; nfields = SALP_NUM_F32; arr = (char*)h->view.f32; *elem = sizeof(float);
+  } else if (field >= SALP_I32_BASE && field < SALP_I32_END) {
+    local = field - SALP_I32_BASE; nfields = SALP_NUM_I32; arr = (char*)h->view.i32; *elem = sizeof(int32_t);
+  } else {
+    return fail(h, SALP_ERR_INVALID, "unknown SalpField id");
   }
-  if (field >= SALP_F32_BASE && field < SALP_F32_END) {
-    *base = (char*)(h->view.f32 + (int64_t)(field - SALP_F32_BASE) * n); *elem = sizeof(float); return SALP_OK;
-  }
-  if (field >= SALP_I32_BASE && field < SALP_I32_END) {
-    *base = (char*)(h->view.i32 + (int64_t)(field - SALP_I32_BASE) * n); *elem = sizeof(int32_t); return SALP_OK;
-  }
-  return fail(h, SALP_ERR_INVALID, "unknown SalpField id");
+#if SALP_STATE_AOS
+  (void)n;
+  *base = arr + *elem * local;
+  *stride = *elem * nfields;
+#else
+  (void)nfields;
+  *base = arr + *elem * local * n;
+  *stride = *elem;
+#endif
+  return SALP_OK;
 }
 
 int salp_get_state(salp_handle h, int32_t field, void* host_dst, int64_t first, int64_t count) {
   if (!h || !host_dst || first < 0 || count < 0 || first + count > h->view.n) return SALP_ERR_INVALID;
   DeviceGuard g(h->device);
-  char* base; size_t elem;
-  int rc = column_of(h, field, &base, &elem);
+  char* base; size_t elem, stride;
+  int rc = column_of(h, field, &base, &elem, &stride);
   if (rc) return rc;
   CU(h, cudaDeviceSynchronize());
-  CU(h, cudaMemcpy(host_dst, base + elem * first, elem * count, cudaMemcpyDeviceToHost));
+  if (count) CU(h, cudaMemcpy2D(host_dst, elem, base + stride * first, stride, elem, (size_t)count, cudaMemcpyDeviceToHost));
   return SALP_OK;
 }
 
 int salp_set_state(salp_handle h, int32_t field, const void* host_src, int64_t first, int64_t count) {
   if (!h || !host_src || first < 0 || count < 0 || first + count > h->view.n) return SALP_ERR_INVALID;
   DeviceGuard g(h->device);
-  char* base; size_t elem;
-  int rc = column_of(h, field, &base, &elem);
+  char* base; size_t elem, stride;
+  int rc = column_of(h, field, &base, &elem, &stride);
   if (rc) return rc;
   CU(h, cudaDeviceSynchronize());
-  CU(h, cudaMemcpy(base + elem * first, host_src, elem * count, cudaMemcpyHostToDevice));
+  if (count) CU(h, cudaMemcpy2D(base + stride * first, stride, host_src, elem, elem, (size_t)count, cudaMemcpyHostToDevice));
   return SALP_OK;
 }
 
-int salp_state_ptr(salp_handle h, int32_t field, void** dev_ptr) {
-  if (!h || !dev_ptr) return SALP_ERR_INVALID;
-  char* base; size_t elem;
-  int rc = column_of(h, field, &base, &elem);
+int salp_state_ptr(salp_handle h, int32_t field, void** dev_ptr, int64_t* stride_bytes) {
+  if (!h || !dev_ptr || !stride_bytes) return SALP_ERR_INVALID;
+  char* base; size_t elem, stride;
+  int rc = column_of(h, field, &base, &elem, &stride);
   if (rc) return rc;
   *dev_ptr = base;
+  *stride_bytes = (int64_t)stride;
   return SALP_OK;
 }
 

@@ -9,13 +9,19 @@
 #include "salp_loop_f64.cuh"
 #include "salp_loop_mixed.cuh"
 
-// column accessors (SoA, env index fastest)
+// state accessors of env i (record-per-env layout, see salp_common.cuh)
 struct Cols {
   const SalpView& v;
   int64_t i;
+#if SALP_STATE_AOS
+  SALP_HD double& d(int f) const { return v.f64[i * SALP_NUM_F64_FIELDS + f]; }
+  SALP_HD float& f(int f) const { return v.f32[i * SALP_NUM_F32 + (f - SALP_F32_BASE)]; }
+  SALP_HD int32_t& n(int f) const { return v.i32[i * SALP_NUM_I32 + (f - SALP_I32_BASE)]; }
+#else
   SALP_HD double& d(int f) const { return v.f64[(int64_t)f * v.n + i]; }
   SALP_HD float& f(int f) const { return v.f32[(int64_t)(f - SALP_F32_BASE) * v.n + i]; }
   SALP_HD int32_t& n(int f) const { return v.i32[(int64_t)(f - SALP_I32_BASE) * v.n + i]; }
+#endif
 };
 
 SALP_HD double norm2d(double x, double y) { return sqrt(x * x + y * y); }

@@ -138,7 +138,7 @@ typedef enum SalpEpisodeMetric {
 /*
  * Per-env state columns readable / writable through salp_get_state / salp_set_state
  * (used by the parity tests to inject and compare state; names follow robot.py).
- * All F64 columns are double[N], F32 float[N], I32 int32_t[N].
+ * All F64 fields are double, F32 float, I32 int32_t, one value per env.
  */
 typedef enum SalpField {
   /* F64: Robot motion state, robot.py:358-374 */
@@ -240,11 +240,12 @@ int salp_step_host(salp_handle h, const SalpStepIO* io_host, uint32_t flags);
 int salp_set_scene_pool(salp_handle h, const float* targets_host, const float* obstacles_host,
                         int64_t scenes_per_env);
 
-/* Copy one state column to / from host memory (synchronous). `count` envs from `first`. */
+/* Copy one state field of `count` envs from `first` to / from a DENSE host array (synchronous). */
 int salp_get_state(salp_handle h, int32_t field, void* host_dst, int64_t first, int64_t count);
 int salp_set_state(salp_handle h, int32_t field, const void* host_src, int64_t first, int64_t count);
-/* Raw device pointer of a column (zero-copy views for torch / cupy). */
-int salp_state_ptr(salp_handle h, int32_t field, void** dev_ptr);
+/* Raw device address of env 0's element of a field and the byte stride between consecutive envs
+ * (state is stored as one record per env): zero-copy strided views for torch / cupy. */
+int salp_state_ptr(salp_handle h, int32_t field, void** dev_ptr, int64_t* stride_bytes);
 
 /* History feed -- replaces Robot.enable_history_recording() + the per-substep histories of
  * Robot.step_through_cycle (robot.py:681-776) that SalpRobotEnv.step hands out as

@@ -104,23 +104,35 @@ int salp_set_scene_pool(salp_handle h, const float* t, const float* o, int64_t P
   return SALP_OK;
 }
 
-static int column_of(SalpSim* h, int32_t field, char** base, size_t* elem) {
+static int column_of(SalpSim* h, int32_t field, char** base, size_t* elem, size_t* stride) {
   const int64_t n = h->view.n;
-  if (field >= 0 && field < SALP_NUM_F64_FIELDS) { *base = (char*)(h->view.f64 + (int64_t)field * n); *elem = 8; return 0; }
-  if (field >= SALP_F32_BASE && field < SALP_F32_END) { *base = (char*)(h->view.f32 + (int64_t)(field - SALP_F32_BASE) * n); *elem = 4; return 0; }
-  if (field >= SALP_I32_BASE && field < SALP_I32_END) { *base = (char*)(h->view.i32 + (int64_t)(field - SALP_I32_BASE) * n); *elem = 4; return 0; }
-  return SALP_ERR_INVALID;
+  int64_t local, nfields;
+  char* arr;
+  if (field >= 0 && field < SALP_NUM_F64_FIELDS) { local = field; nfields = SALP_NUM_F64_FIELDS; arr = (char*)h->view.f64; *elem = 8; }
+  else if (field >= SALP_F32_BASE && field < SALP_F32_END) { local = field - SALP_F32_BASE; nfields = SALP_NUM_F32; arr = (char*)h->view.f32; *elem = 4; }
+  else if (field >= SALP_I32_BASE && field < SALP_I32_END) { local = field - SALP_I32_BASE; nfields = SALP_NUM_I32; arr = (char*)h->view.i32; *elem = 4; }
+  else return SALP_ERR_INVALID;
+#if SALP_STATE_AOS
+  (void)n;
+  *base = arr + *elem * local;
+  *stride = *elem * nfields;
+#else
+  (void)nfields;
+  *base = arr + *elem * local * n;
+  *stride = *elem;
+#endif
+  return 0;
 }
 int salp_get_state(salp_handle h, int32_t field, void* dst, int64_t first, int64_t count) {
-  char* base; size_t elem;
-  if (!h || column_of(h, field, &base, &elem)) return SALP_ERR_INVALID;
-  memcpy(dst, base + elem * first, elem * count);
+  char* base; size_t elem, stride;
+  if (!h || column_of(h, field, &base, &elem, &stride)) return SALP_ERR_INVALID;
+  for (int64_t k = 0; k < count; k++) memcpy((char*)dst + elem * k, base + stride * (first + k), elem);
   return SALP_OK;
 }
 int salp_set_state(salp_handle h, int32_t field, const void* src, int64_t first, int64_t count) {
-  char* base; size_t elem;
-  if (!h || column_of(h, field, &base, &elem)) return SALP_ERR_INVALID;
-  memcpy(base + elem * first, src, elem * count);
+  char* base; size_t elem, stride;
+  if (!h || column_of(h, field, &base, &elem, &stride)) return SALP_ERR_INVALID;
+  for (int64_t k = 0; k < count; k++) memcpy(base + stride * (first + k), (const char*)src + elem * k, elem);
   return SALP_OK;
 }
 int salp_trace_cycle(salp_handle h, int64_t env, const float* a, double* trace, int32_t capacity, int32_t* K_out) {
