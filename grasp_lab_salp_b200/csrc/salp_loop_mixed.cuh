@@ -14,9 +14,9 @@
 //    difference is exactly 0 in the reference too, and the ~30 geometry-derived coefficients
 //    stay in registers (phase-specialised loop, SURVEY.md hard part 3).
 //  * Integrals that grow over an episode (world position, body-frame position/angle integrals,
-//    the three Euler angles) are two-level sums: an fp32 partial per 16-substep chunk, flushed
+//    the three Euler angles) are two-level sums: an fp32 partial per 32-substep chunk, flushed
 //    into an fp64 total.  sin/cos of each Euler angle is carried as a pair that is rotated by the
-//    small per-substep increment (10-instruction Taylor kernels, no range reduction) and
+//    small per-substep increment (5-instruction Taylor kernels, no range reduction) and
 //    re-anchored from the fp64 total at every flush, so it is valid for any angle.
 //  * kin(k-1) and dyn(k) are software-pipelined into one basic block (two independent chains).
 //  * The substep count K and the phase of every substep are decided exactly as the reference
