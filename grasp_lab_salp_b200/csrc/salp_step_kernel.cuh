@@ -30,10 +30,20 @@ salp_step_kernel(const __grid_constant__ SalpParams p, const __grid_constant__ S
   env_step<PREC>(p, dv, v, io, flags, i);
 }
 
-static inline int block_for(int64_t n) {
-  // small batches: one warp per block so that the warps spread over all 148 SMs
-  return n <= 148 * 4 * 32 ? 32 : 128;
+// Kernel choice by batch size.  Up to SALP_LAT_MAX_ENVS the latency build (one warp per block,
+// <= 255 registers, 9 warps per SM) is used; beyond that the throughput build (128-thread blocks,
+// 128 registers, 16 warps per SM).  The crossover was measured (tools/diag_crossover.py); the
+// environment variable SALP_LAT_MAX_ENVS overrides it for experiments.
+#include <cstdlib>
+static inline int64_t salp_lat_max_envs() {
+  static int64_t cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("SALP_LAT_MAX_ENVS");
+    cached = e ? atoll(e) : (int64_t)148 * 4 * 32;
+  }
+  return cached;
 }
+static inline int block_for(int64_t n) { return n <= salp_lat_max_envs() ? 32 : 128; }
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
 

@@ -9,7 +9,7 @@ import torch
 from grasp_lab_salp_b200 import SalpBatch, default_params
 
 dev = torch.device('cuda', 0)
-for n in (4096, 8192, 12288, 16384, 18944, 20480, 24576, 32768, 49152):
+for n in (18944, 24576, 32768, 42624, 49152, 65536, 98304, 131072):
     b = SalpBatch(n, default_params(), seed=0)
     b.reset_device()
     g = torch.Generator(device=dev)
