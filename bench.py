@@ -257,6 +257,7 @@ def run_cuda_arm(args):
     import torch.distributed as dist
 
     from grasp_lab_salp_b200 import PRECISION_F64, PRECISION_MIXED, SalpBatch, _lib, default_params
+    from grasp_lab_salp_b200.params import sort_by_k_auto
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -309,7 +310,7 @@ def run_cuda_arm(args):
 
     def sort_flag(n_envs):
         if args.sort_by_k == "auto":
-            return n_envs >= 32768          # below that the GPU is not full and the longest warp decides
+            return sort_by_k_auto(n_envs)    # one warp per SM sub-partition or less: the longest warp decides
         return args.sort_by_k == "on"
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2

@@ -65,6 +65,16 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
     os.makedirs(OBJ_DIR, exist_ok=True)
+    # ranks of one torchrun job may find the library stale together: one builds, the rest wait
+    import fcntl
+    with open(os.path.join(OBJ_DIR, "build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not is_stale():
+            return LIB
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose: bool) -> str:
     objs = []
     log = []
     for unit, extra in UNITS.items():
@@ -76,12 +86,13 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(log[-1])
             raise RuntimeError(f"nvcc failed on {unit}")
         objs.append(obj)
-    cmd = [nvcc(), *ARCH, "-shared", "-o", LIB, *objs, "-Xlinker", "--exclude-libs,ALL"]
+    cmd = [nvcc(), *ARCH, "-shared", "-o", LIB + ".tmp", *objs, "-Xlinker", "--exclude-libs,ALL"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if r.returncode != 0:
         sys.stderr.write(log[-1])
         raise RuntimeError("link of libsalp_b200.so failed")
+    os.replace(LIB + ".tmp", LIB)
     with open(os.path.join(OBJ_DIR, "build.log"), "w") as f:
         f.write("\n".join(log))
     with open(HASH_FILE, "w") as f:

@@ -4,6 +4,6 @@
 
 void salp_launch_step_f64(const SalpParams& p, const SalpView& v, const SalpStepIO& io, uint32_t flags,
                           const int32_t* order, cudaStream_t stream) {
-  const int block = block_for(v.n);
+  const int block = 128;
   salp_step_kernel<SALP_PRECISION_F64><<<grid_for(v.n, block), block, 0, stream>>>(p, make_derived(p), v, io, flags, order);
 }

@@ -4,10 +4,12 @@
 #pragma once
 #include "salp_env.cuh"
 
-// Two register budgets of the same kernel: the throughput build (<= 128 registers, 16 warps/SM) for
-// batches that fill the GPU, and the latency build (<= 255 registers, used with one warp per
-// block) for small batches, where each SM sub-partition holds at most one warp and only
-// instruction-level parallelism inside that warp hides the FP32 pipe latency.
+// Two register budgets of the same kernel.  The wide build (one warp per block, <= 255 registers,
+// 8 warps per SM) is the default for MIXED at every batch size: the substep loop is bound by
+// instruction issue, not by latency, so 8 warps with the whole working set in registers run as
+// fast as 16 warps at 128 registers on full GPUs (1M envs: 6.48 vs 6.51 ms) and up to 1.45x
+// faster on partial waves (42k envs: 0.37 vs 0.53 ms; profiles/README.md, "kernel choice").
+// The 128-register build remains for F64 (FP64-pipe bound) and as an experiment switch.
 template <int PREC>
 __global__ void __launch_bounds__(32, 1)
 salp_step_kernel_lat(const __grid_constant__ SalpParams p, const __grid_constant__ SalpDerived dv,
@@ -30,16 +32,14 @@ salp_step_kernel(const __grid_constant__ SalpParams p, const __grid_constant__ S
   env_step<PREC>(p, dv, v, io, flags, i);
 }
 
-// Kernel choice by batch size.  Up to SALP_LAT_MAX_ENVS the latency build (one warp per block,
-// <= 255 registers, 9 warps per SM) is used; beyond that the throughput build (128-thread blocks,
-// 128 registers, 16 warps per SM).  The crossover was measured (tools/diag_crossover.py); the
-// environment variable SALP_LAT_MAX_ENVS overrides it for experiments.
+// Kernel choice: the wide build up to SALP_LAT_MAX_ENVS envs (default: always); the environment
+// variable exists to reproduce the crossover measurement of tools/diag_crossover.py.
 #include <cstdlib>
 static inline int64_t salp_lat_max_envs() {
   static int64_t cached = -1;
   if (cached < 0) {
     const char* e = getenv("SALP_LAT_MAX_ENVS");
-    cached = e ? atoll(e) : (int64_t)148 * 4 * 32;
+    cached = e ? atoll(e) : INT64_MAX;
   }
   return cached;
 }

@@ -33,6 +33,8 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from .params import sort_by_k_auto
+
 
 # ------------------------------------------------------------------------------------------------
 # env adapters
@@ -44,7 +46,7 @@ class DeviceEnv:
         self.batch = batch
         self.num_envs, self.obs_dim = batch.num_envs, batch.obs_dim
         self.device = torch.device("cuda", batch.device)
-        self.sort = batch.num_envs >= 32768 if sort_by_k == "auto" else bool(sort_by_k)
+        self.sort = sort_by_k_auto(batch.num_envs) if sort_by_k == "auto" else bool(sort_by_k)
 
     def reset_t(self):
         return self.batch.reset_device().clone()

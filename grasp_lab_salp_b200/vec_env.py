@@ -21,7 +21,7 @@ import numpy as np
 
 from . import spaces
 from .batch import SalpBatch
-from .params import EPISODE_METRIC_NAMES, REWARD_TERM_NAMES, SalpParams, default_params
+from .params import EPISODE_METRIC_NAMES, REWARD_TERM_NAMES, SalpParams, default_params, sort_by_k_auto
 
 try:  # pragma: no cover - depends on the environment
     from stable_baselines3.common.vec_env import VecEnv as _SB3VecEnv
@@ -51,7 +51,7 @@ class _VecEnvSurface:
         self._seed = seed
         self._t_start = time.time()
         if sort_by_k == "auto":
-            sort_by_k = self.num_envs >= 32768
+            sort_by_k = sort_by_k_auto(self.num_envs)
         self._sort = bool(sort_by_k)
         if info_mode not in ("full", "lazy", "auto"):
             raise ValueError("info_mode must be 'full', 'lazy' or 'auto'")

@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE ONLY: host build of the device step body (see salp_emu.cu)."""
 from __future__ import annotations
 
+import fcntl
 import hashlib
 import os
 import shutil
@@ -30,16 +31,31 @@ def build(lane_only: bool = False) -> str:
     lib = os.path.join(OUT, "libsalp_emu_lane.so") if lane_only else LIB
     stamp = lib + ".hash"
     d = _digest()
-    if os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == d:
+
+    def fresh():
+        return os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == d
+
+    if fresh():
         return lib
+    # several test processes (the 2-rank gloo tests) may get here together: one builds, into a
+    # temporary name, the others wait on the lock and then find the fresh library
+    with open(lib + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if fresh():
+            return lib
+        return _compile(lib, stamp, d, lane_only)
+
+
+def _compile(lib, stamp, d, lane_only):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     # host code is what runs; the (unused) device pass still needs an arch.  No contraction on the
     # host so that fp32/fp64 products and sums round separately, like the oracle build.
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-shared",
            *(["-DSALP_EMU_LANE_ONLY"] if lane_only else []),
-           "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-mfma", "-o", lib,
+           "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-mfma", "-o", lib + ".tmp",
            os.path.join(HERE, "salp_emu.cu")]
     subprocess.run(cmd, check=True, capture_output=True, text=True)
+    os.replace(lib + ".tmp", lib)
     with open(stamp, "w") as f:
         f.write(d)
     return lib

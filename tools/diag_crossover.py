@@ -9,7 +9,8 @@ import torch
 from grasp_lab_salp_b200 import SalpBatch, default_params
 
 dev = torch.device('cuda', 0)
-for n in (18944, 24576, 32768, 42624, 49152, 65536, 98304, 131072):
+import os
+for n in [int(x) for x in os.environ.get('DIAG_NS','18944,24576,32768,42624,49152,65536,98304,131072').split(',')]:
     b = SalpBatch(n, default_params(), seed=0)
     b.reset_device()
     g = torch.Generator(device=dev)
