@@ -296,6 +296,35 @@ int salp_reset_host(salp_handle h, const uint8_t* mask_host, float* obs_host) {
   return SALP_OK;
 }
 
+// Device-side alias of a caller's HOST buffer, if it has one: page-locked memory (cudaHostAlloc /
+// cudaHostRegister, torch's pin_memory) is mapped into the device address space under unified
+// addressing.  Pageable memory (a plain numpy array) has none -> nullptr, the staged path is used.
+static void* mapped_alias(const void* host_ptr) {
+  if (!host_ptr) return nullptr;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host_ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+  return at.devicePointer;
+}
+static bool zero_copy_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("SALP_ZERO_COPY"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on != 0;
+}
+
+// Host-buffer step.  Two transports, chosen per call from the caller's pointers:
+//  * zero-copy (page-locked caller buffers, MIXED precision): the step kernel stores obs / reward /
+//    flags / terminal obs straight into the caller's memory as each warp finishes -- the transfer
+//    overlaps the integration of the other warps and no copy is queued behind the kernel.  The
+//    kernel only ever WRITES those arrays (observation rows are assembled in shared memory).
+//    Actions are read in place for batches of at most one warp per SM sub-partition and staged by
+//    the copy engine above that (the K-sort reads them a second time).
+//  * staged (pageable caller buffers, or F64 / pipeline kernels): H2D of the actions, kernel on
+//    the handle's own device buffers, one D2H per output.
+// The optional extras (reward_terms, substeps, episode_metrics) are always staged.
 int salp_step_host(salp_handle h, const SalpStepIO* io, uint32_t flags) {
   if (!h || !io) return SALP_ERR_INVALID;
   if (!io->actions || !io->obs || !io->reward || !io->terminated || !io->truncated)
@@ -304,25 +333,33 @@ int salp_step_host(salp_handle h, const SalpStepIO* io, uint32_t flags) {
   cudaStream_t s = h->host_stream;
   const int64_t n = h->view.n;
   const int D = h->obs_dim;
-  CU(h, cudaMemcpyAsync(h->d_actions, io->actions, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, s));
+  const bool zc_ok = zero_copy_enabled() && h->params.precision == SALP_PRECISION_MIXED && !(flags & SALP_STEP_PIPELINE);
+  float* z_obs = zc_ok ? (float*)mapped_alias(io->obs) : nullptr;
+  float* z_reward = zc_ok ? (float*)mapped_alias(io->reward) : nullptr;
+  uint8_t* z_term = zc_ok ? (uint8_t*)mapped_alias(io->terminated) : nullptr;
+  uint8_t* z_trunc = zc_ok ? (uint8_t*)mapped_alias(io->truncated) : nullptr;
+  float* z_tobs = zc_ok ? (float*)mapped_alias(io->terminal_obs) : nullptr;
+  const float* z_act = (zc_ok && !(flags & SALP_STEP_SORT_BY_K) && n <= (int64_t)148 * 4 * 32)
+                           ? (const float*)mapped_alias(io->actions) : nullptr;
+  if (!z_act) CU(h, cudaMemcpyAsync(h->d_actions, io->actions, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, s));
   SalpStepIO d;
-  d.actions = h->d_actions;
-  d.obs = h->d_obs;
-  d.reward = h->d_reward;
-  d.terminated = h->d_terminated;
-  d.truncated = h->d_truncated;
-  d.terminal_obs = io->terminal_obs ? h->d_terminal_obs : nullptr;
+  d.actions = z_act ? z_act : h->d_actions;
+  d.obs = z_obs ? z_obs : h->d_obs;
+  d.reward = z_reward ? z_reward : h->d_reward;
+  d.terminated = z_term ? z_term : h->d_terminated;
+  d.truncated = z_trunc ? z_trunc : h->d_truncated;
+  d.terminal_obs = io->terminal_obs ? (z_tobs ? z_tobs : h->d_terminal_obs) : nullptr;
   d.reward_terms = io->reward_terms ? h->d_terms : nullptr;
   d.substeps = io->substeps ? h->d_substeps : nullptr;
   d.episode_metrics = io->episode_metrics ? h->d_metrics : nullptr;
   int rc = salp_launch_step(h->params, h->view, d, flags, h->scratch, s);
   if (rc < 0) return cuda_fail(h, cudaGetLastError(), "salp_step_host launch");
   h->launches += rc;
-  CU(h, cudaMemcpyAsync(io->obs, d.obs, sizeof(float) * D * n, cudaMemcpyDeviceToHost, s));
-  CU(h, cudaMemcpyAsync(io->reward, d.reward, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
-  CU(h, cudaMemcpyAsync(io->terminated, d.terminated, n, cudaMemcpyDeviceToHost, s));
-  CU(h, cudaMemcpyAsync(io->truncated, d.truncated, n, cudaMemcpyDeviceToHost, s));
-  if (io->terminal_obs)
+  if (!z_obs) CU(h, cudaMemcpyAsync(io->obs, d.obs, sizeof(float) * D * n, cudaMemcpyDeviceToHost, s));
+  if (!z_reward) CU(h, cudaMemcpyAsync(io->reward, d.reward, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+  if (!z_term) CU(h, cudaMemcpyAsync(io->terminated, d.terminated, n, cudaMemcpyDeviceToHost, s));
+  if (!z_trunc) CU(h, cudaMemcpyAsync(io->truncated, d.truncated, n, cudaMemcpyDeviceToHost, s));
+  if (io->terminal_obs && !z_tobs)
     CU(h, cudaMemcpyAsync(io->terminal_obs, d.terminal_obs, sizeof(float) * D * n, cudaMemcpyDeviceToHost, s));
   if (io->reward_terms)
     CU(h, cudaMemcpyAsync(io->reward_terms, d.reward_terms, sizeof(double) * SALP_NUM_REWARD_TERMS * n,

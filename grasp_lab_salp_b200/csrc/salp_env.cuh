@@ -289,10 +289,20 @@ SALP_HD void env_step_begin(const SalpParams& p, const SalpView& v, const SalpSt
 
 // `pos0` / `ang0`: body-frame integrals at the START of the cycle (they become prev_position /
 // prev_angle, robot.py:747-748); K, t: substeps run and cycle_time reached.
+//
+// `obs_row` / `tobs_row`: where this env's observation and terminal observation are assembled.  The
+// default is their final place in io.obs / io.terminal_obs; the step kernel passes rows of a
+// shared-memory tile instead and writes the tile out warp-wide afterwards -- coalesced, and
+// without ever READING the output arrays, which may then be mapped host memory (salp_step_host).
 SALP_HD void env_step_end(const SalpParams& p, const SalpView& v, const SalpStepIO& io, uint32_t flags, int64_t i,
-                          const StepCtx& cx, const double pos0[3], const double ang0[3], Body64& b, int K, double t) {
+                          const StepCtx& cx, const double pos0[3], const double ang0[3], Body64& b, int K, double t,
+                          float* obs_row = nullptr, float* tobs_row = nullptr) {
   Cols c{v, i};
   const int D = SALP_OBS_BASE + 2 * p.num_obstacles;
+  if (!obs_row) {
+    obs_row = io.obs + i * D;
+    tobs_row = io.terminal_obs ? io.terminal_obs + i * D : nullptr;
+  }
   const CyclePlan& plan = cx.plan;
   const float a0 = cx.a0, a1 = cx.a1, a2 = cx.a2;
   const double avg_vy = cx.avg_vy, avg_wz = cx.avg_wz, last_x = cx.last_x, last_y = cx.last_y;
@@ -378,7 +388,7 @@ SALP_HD void env_step_end(const SalpParams& p, const SalpView& v, const SalpStep
   double rew = terms[0] + terms[1] + terms[2] + terms[3] + terms[4] + terms[5] + terms[6];
 
   // :250  observation
-  float* obs = io.obs + i * D;
+  float* obs = obs_row;
   obs[0] = (float)bx;                                   // _get_observation (:651-670), sharing R and the heading
   obs[1] = (float)by;
   obs[2] = (float)b.v[0];
@@ -440,8 +450,8 @@ SALP_HD void env_step_end(const SalpParams& p, const SalpView& v, const SalpStep
     io.reward_terms[8 * i + 7] = rew;
   }
   if (io.substeps) io.substeps[i] = K < 0 ? SALP_MAX_SUBSTEPS : K;
-  if (io.terminal_obs)
-    for (int k = 0; k < D; k++) io.terminal_obs[i * D + k] = obs[k];
+  if (tobs_row)
+    for (int k = 0; k < D; k++) tobs_row[k] = obs[k];
   // SB3 VecEnv worker semantics: reset the finished env, hand back the post-reset observation
   if ((flags & SALP_STEP_AUTORESET) && ended) env_reset(p, v, i, obs);
 }
@@ -473,7 +483,7 @@ SALP_HD int env_trace_cycle(const SalpParams& p, const SalpView& v, int64_t i, f
 
 template <int PREC>
 SALP_HD void env_step(const SalpParams& p, const SalpDerived& dv, const SalpView& v, const SalpStepIO& io,
-                      uint32_t flags, int64_t i) {
+                      uint32_t flags, int64_t i, float* obs_row = nullptr, float* tobs_row = nullptr) {
   StepCtx cx;
   Body64 b;
   env_step_begin(p, v, io, i, cx, b);
@@ -481,5 +491,5 @@ SALP_HD void env_step(const SalpParams& p, const SalpDerived& dv, const SalpView
   const double ang0[3] = {b.ang[0], b.ang[1], b.ang[2]};
   double t = 0.0;
   const int K = run_cycle<PREC>(p, dv, cx.plan, v.time_table, b, t, &cx.rc);
-  env_step_end(p, v, io, flags, i, cx, pos0, ang0, b, K, t);
+  env_step_end(p, v, io, flags, i, cx, pos0, ang0, b, K, t, obs_row, tobs_row);
 }

@@ -127,6 +127,34 @@ def test_device_face_equals_host_face():
     np.testing.assert_array_equal(v.cpu().numpy(), host.get_state("posw_x"))
 
 
+@pytest.mark.parametrize("sort", [False, True])
+def test_zero_copy_host_path_equals_staged_host_path(sort):
+    """salp_step_host writes straight into page-locked caller buffers (mapped host memory, rows
+    assembled in shared memory) and stages through device buffers for pageable ones: same bits.
+    The last warp is ragged (n % 32 != 0) and the batch ends/auto-resets episodes on the way."""
+    n, T = 1000, 12
+    g = load_golden("ref_random.npz")
+    acts = uniform_actions(np.random.default_rng(8), T, n)
+    pinned = SalpBatch(n, golden_params(g), seed=3)
+    paged = SalpBatch(n, golden_params(g), seed=3)
+    for name in ("obs", "terminal_obs", "reward", "terminated", "truncated"):
+        setattr(paged, name, np.full_like(getattr(paged, name), 7))       # plain numpy: not page-locked
+    a_pinned = pinned.host_buffer((n, 3), np.float32)
+    np.testing.assert_array_equal(pinned.reset(), paged.reset())
+    ended = 0
+    for t in range(T):
+        a_pinned[:] = acts[t]
+        o, r, te, tr = pinned.step(a_pinned, auto_reset=True, sort_by_k=sort)
+        o2, r2, te2, tr2 = paged.step(acts[t].copy(), auto_reset=True, sort_by_k=sort)
+        for x, y in ((o, o2), (r, r2), (te, te2), (tr, tr2), (pinned.terminal_obs, paged.terminal_obs),
+                     (pinned.substeps, paged.substeps), (pinned.terms, paged.terms)):
+            np.testing.assert_array_equal(x, y)
+        ended += int((te | tr).sum())
+    assert ended > 0
+    pinned.check()
+    paged.check()
+
+
 def test_full_size_mixed_vs_f64_trajectory_equivalence():
     """BASELINE config 2 shape (4096 envs, random actions, auto-reset), free-running: the fp32
     kernel against the float64 kernel on every env.  Integer quantities must agree exactly on
