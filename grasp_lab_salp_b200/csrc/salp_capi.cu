@@ -321,8 +321,8 @@ static bool zero_copy_enabled() {
 //    overlaps the integration of the other warps and no copy is queued behind the kernel.  The
 //    kernel only ever WRITES those arrays (observation rows are assembled in shared memory).
 //    Actions are read in place for batches of at most one warp per SM sub-partition and staged by
-//    the copy engine above that (the K-sort reads them a second time).
-//  * staged (pageable caller buffers, or F64 / pipeline kernels): H2D of the actions, kernel on
+//    the copy engine above that.  Used for steps in natural env order only.
+//  * staged (pageable caller buffers, K-sorted steps, F64 / pipeline kernels): H2D of the actions, kernel on
 //    the handle's own device buffers, one D2H per output.
 // The optional extras (reward_terms, substeps, episode_metrics) are always staged.
 int salp_step_host(salp_handle h, const SalpStepIO* io, uint32_t flags) {
@@ -333,13 +333,16 @@ int salp_step_host(salp_handle h, const SalpStepIO* io, uint32_t flags) {
   cudaStream_t s = h->host_stream;
   const int64_t n = h->view.n;
   const int D = h->obs_dim;
-  const bool zc_ok = zero_copy_enabled() && h->params.precision == SALP_PRECISION_MIXED && !(flags & SALP_STEP_PIPELINE);
+  // (K-sorted steps visit the envs in scattered order: 40-byte rows make poor PCIe writes --
+  //  measured 12.7 ms vs 8.2 ms staged at 1 M envs -- so they keep the staged transport)
+  const bool zc_ok = zero_copy_enabled() && h->params.precision == SALP_PRECISION_MIXED &&
+                     !(flags & (SALP_STEP_PIPELINE | SALP_STEP_SORT_BY_K));
   float* z_obs = zc_ok ? (float*)mapped_alias(io->obs) : nullptr;
   float* z_reward = zc_ok ? (float*)mapped_alias(io->reward) : nullptr;
   uint8_t* z_term = zc_ok ? (uint8_t*)mapped_alias(io->terminated) : nullptr;
   uint8_t* z_trunc = zc_ok ? (uint8_t*)mapped_alias(io->truncated) : nullptr;
   float* z_tobs = zc_ok ? (float*)mapped_alias(io->terminal_obs) : nullptr;
-  const float* z_act = (zc_ok && !(flags & SALP_STEP_SORT_BY_K) && n <= (int64_t)148 * 4 * 32)
+  const float* z_act = (zc_ok && n <= (int64_t)148 * 4 * 32)
                            ? (const float*)mapped_alias(io->actions) : nullptr;
   if (!z_act) CU(h, cudaMemcpyAsync(h->d_actions, io->actions, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, s));
   SalpStepIO d;

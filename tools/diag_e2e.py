@@ -19,7 +19,7 @@ for n in [int(x) for x in os.environ.get("DIAG_NS", "4096,16384,65536,262144,104
     for a in acts:
         a[:] = rng.uniform([0, 0, -1], [1, 1, 1], size=(n, 3))
     sort = sort_by_k_auto(n)
-    for i in range(5):
+    for i in range(int(os.environ.get('DIAG_WARMUP', '300')) if n <= 65536 else 5):
         b.step(acts[i % 4], auto_reset=True, sort_by_k=sort, extras=False)
     steps = 60 if n <= 65536 else 15
     t0 = time.perf_counter()
