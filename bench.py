@@ -367,7 +367,8 @@ def run_cuda_arm(args):
         D = params.obs_dim
         e2e = {"value": total_env_steps / dt, "unit": METRIC, "h2d_bytes_per_step": n * 3 * 4,
                "d2h_bytes_per_step": n * (D * 4 * 2 + 4 + 1 + 1), "ms_per_step": 1e3 * dt / args.steps,
-               "api": "SalpBatch.step -> salp_step_host (pinned host buffers, wall clock around synchronous calls)"}
+               "api": "SalpBatch.step -> salp_step_host (page-locked host buffers, wall clock around synchronous calls; "
+                      + ("staged H2D/D2H copies" if sort_flag(n) else "kernel reads/writes the mapped host buffers directly") + ")"}
         hb.close()
 
     # ---- env-count sweep (BASELINE config 5) : where the GPU saturates ----

@@ -226,8 +226,13 @@ int salp_reset(salp_handle h, const uint8_t* mask_dev, float* obs_dev, void* str
  * with non-finite entries replaced by 0, episode metric SALP_EM_NONFINITE = 1). */
 int salp_step(salp_handle h, const SalpStepIO* io_dev, uint32_t flags, void* stream);
 
-/* Same two calls with HOST buffers: H2D of actions, the kernels, D2H of every non-null
- * output, one stream synchronise.  This is what a numpy-facing VecEnv calls. */
+/* Same two calls with HOST buffers; they return when the results are in the caller's memory
+ * (one stream synchronise).  This is what a numpy-facing VecEnv calls.  Any host memory works.
+ * Transport of salp_step_host: for PAGE-LOCKED buffers (cudaHostAlloc / cudaHostRegister, e.g.
+ * torch's pin_memory) in SALP_PRECISION_MIXED without SALP_STEP_SORT_BY_K the kernel writes obs,
+ * reward, flags and terminal obs directly into the caller's memory while it runs (and reads the
+ * actions in place for N <= 18944); otherwise H2D of the actions, the kernels on internal device
+ * buffers, one D2H per non-null output.  Results are bit-identical either way. */
 int salp_reset_host(salp_handle h, const uint8_t* mask_host, float* obs_host);
 int salp_step_host(salp_handle h, const SalpStepIO* io_host, uint32_t flags);
 
