@@ -392,6 +392,33 @@ def run_cuda_arm(args):
             b.close()
             del b, p
 
+    # ---- synthetic input B: actions of a random-init Gaussian policy, N(0, 1) clipped to
+    # the Box -> ~50 % of a0/a1 are exactly 0 and ~16 % exactly 1: bimodal K ----
+    input_b = None
+    if not args.no_sweep:
+        input_b = []
+        for ne in sorted({n, 262144}):
+            b = make_batch(ne)
+            g = torch.Generator(device=dev)
+            g.manual_seed(4321 + rank)
+            p = torch.randn((8, ne, 3), generator=g, device=dev, dtype=torch.float32)
+            p[..., :2].clamp_(0.0, 1.0)
+            p[..., 2].clamp_(-1.0, 1.0)
+            st = max(5, min(40, int(4e6 // ne) + 5))
+            m, ssum, _ = time_steps(torch, b, p.contiguous(), st, 3, sort_flag(ne), flush)
+            b.step_device(p[0], auto_reset=True, sort_by_k=sort_flag(ne), extras=True)
+            K = b.dev["substeps"].float()
+            edges = [0, 1, 50, 150, 350, 700, 1000, 1200, 1349]
+            hist = torch.histogram(K.cpu(), bins=torch.tensor(edges, dtype=torch.float32))[0]
+            m = max_over_ranks(m)
+            input_b.append({"envs_per_gpu": ne, "steps": st, "sort_by_k": sort_flag(ne),
+                            "env_steps_per_sec": sum_over_ranks(float(ne * st)) / (m * 1e-3),
+                            "substeps_per_sec": sum_over_ranks(float(ssum)) / (m * 1e-3),
+                            "mean_substeps_per_env_step": float(ssum) / (ne * st),
+                            "K_histogram": {"edges": edges, "share": [round(float(x) / ne, 4) for x in hist]}})
+            b.close()
+            del b, p
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args.cpu_seconds, total_envs=n)
@@ -411,7 +438,7 @@ def run_cuda_arm(args):
                          "peak_source": ("measured in this run: salp_probe_fp32_peak (FFMA, 2048 thr/SM)"
                                          if fp32_peak else "nominal"),
                          "nominal_peak": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved_tf / NOMINAL_FP32_TFLOPS,
-                         "flop_per_substep": FLOP_PER_SUBSTEP, "kernel": "salp_step_kernel<MIXED>",
+                         "flop_per_substep": FLOP_PER_SUBSTEP, "kernel": "salp_step_kernel_lat<MIXED>" if prec == PRECISION_MIXED else "salp_step_kernel<F64>",
                          "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": hbm_achieved / hbm_peak, "bytes_per_env_step": bytes_per_env_step,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
@@ -423,6 +450,8 @@ def run_cuda_arm(args):
             line["cpu_baseline"] = cpu
         if sweep:
             line["sweep"] = sweep
+        if input_b:
+            line["input_b_gaussian_policy_actions"] = input_b
         emit(line)
     if world > 1:
         dist.destroy_process_group()
