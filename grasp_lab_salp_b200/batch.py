@@ -21,7 +21,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .params import (NUM_EPISODE_METRICS, NUM_REWARD_TERMS, STEP_AUTORESET, STEP_PIPELINE, STEP_SORT_BY_K, SalpParams,
+from .params import (NUM_EPISODE_METRICS, NUM_REWARD_TERMS, STEP_AUTORESET, STEP_FUSED, STEP_PIPELINE, STEP_SORT_BY_K, SalpParams,
                      default_params, field_dtype, field_id)
 
 
@@ -127,7 +127,7 @@ class SalpBatch:
         return self.obs
 
     def step(self, actions, auto_reset: bool = False, sort_by_k: bool = False, extras: bool = True,
-             pipeline: bool = False):
+             pipeline=None):
         a = np.ascontiguousarray(actions, np.float32)
         if a.shape != (self.num_envs, 3):
             raise ValueError(f"actions must have shape [{self.num_envs}, 3]")
@@ -142,7 +142,7 @@ class SalpBatch:
         io.substeps = self.substeps.ctypes.data if extras else None
         io.episode_metrics = self.metrics.ctypes.data if extras else None
         flags = ((STEP_AUTORESET if auto_reset else 0) | (STEP_SORT_BY_K if sort_by_k else 0)
-                 | (STEP_PIPELINE if pipeline else 0))
+                 | (0 if pipeline is None else (STEP_PIPELINE if pipeline else STEP_FUSED)))
         self._check(self._L.salp_step_host(self._h, C.byref(io), flags))
         return self.obs, self.reward, self.terminated, self.truncated
 
@@ -213,7 +213,7 @@ class SalpBatch:
         return bufs["obs"]
 
     def step_device(self, actions, auto_reset: bool = True, sort_by_k: bool = False, extras: bool = False,
-                    pipeline: bool = False):
+                    pipeline=None):
         """actions: float32 CUDA tensor [N,3] on this batch's device.  Asynchronous on the current
         torch stream.  Returns (obs, reward, terminated, truncated) device tensors (reused every
         call); ``self.dev["terminal_obs"]`` etc. hold the rest."""
@@ -233,7 +233,7 @@ class SalpBatch:
         io.reward_terms = bufs["terms"].data_ptr() if extras else None
         io.episode_metrics = bufs["metrics"].data_ptr() if extras else None
         flags = ((STEP_AUTORESET if auto_reset else 0) | (STEP_SORT_BY_K if sort_by_k else 0)
-                 | (STEP_PIPELINE if pipeline else 0))
+                 | (0 if pipeline is None else (STEP_PIPELINE if pipeline else STEP_FUSED)))
         self._check(self._L.salp_step(self._h, C.byref(io), flags, self._stream_ptr(self.device)))
         return bufs["obs"], bufs["reward"], bufs["terminated"], bufs["truncated"]
 

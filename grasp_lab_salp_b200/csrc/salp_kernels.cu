@@ -123,18 +123,20 @@ int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& i
     order = scratch.order;
   }
   const int block = block_for(v.n);
-  // opt-in for small batches that fit one wave of 32-env blocks: the warp-specialised pipeline
-  // (experimental: the fused latency kernel is currently faster, see profiles/README.md)
-  if (p.precision == SALP_PRECISION_MIXED && p.randomization == 0 && !order && (flags & SALP_STEP_PIPELINE) &&
+  // batches that fit one 2-warp block per SM: the shape-producer / motion-consumer pipeline
+  // (salp_pipe_kernel.cuh), unless SALP_STEP_FUSED asks for the one-warp kernel
+  if (p.precision == SALP_PRECISION_MIXED && p.randomization == 0 && !order && !(flags & SALP_STEP_FUSED) &&
       v.n <= (int64_t)32 * (v.sm_count > 0 ? v.sm_count : 148)) {
     static bool configured = false;
     if (!configured) {
+      SalpParams widest = p;
+      widest.num_obstacles = SALP_MAX_OBSTACLES;
       if (cudaFuncSetAttribute(salp_step_kernel_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)sizeof(PipeShared)) != cudaSuccess)
+                               (int)pipe_smem_bytes(widest)) != cudaSuccess)
         return SALP_ERR_CUDA;
       configured = true;
     }
-    salp_step_kernel_pipe<<<grid_for(v.n, 32), SALP_PIPE_THREADS, sizeof(PipeShared), stream>>>(p, make_derived(p), v, io, flags);
+    salp_step_kernel_pipe<<<grid_for(v.n, 32), SALP_PIPE_THREADS, pipe_smem_bytes(p), stream>>>(p, make_derived(p), v, io, flags);
     SALP_LAUNCH_CHECK();
     return launches + 1;
   }

@@ -1,89 +1,70 @@
-// salp_pipe_kernel.cuh -- the small-batch step kernel: a warp-specialised, feed-forward pipeline.
+// salp_pipe_kernel.cuh -- the small-batch step kernel: shape producer warp + motion consumer warp.
 //
 // With a few thousand envs the GPU is almost empty (4096 envs = 128 warps on 592 SM sub-partitions)
-// and the step time is K_max (~1340 substeps of the slowest env) x the latency of ONE warp's
-// substep.  The fused kernel issues ~250 instructions per substep from a single warp.  But the
-// substep is feed-forward:
-//
-//     shape(j)  ->  dyn(j)  ->  kin(j)
-//
-//   * the body shape and every coefficient derived from it depend on the action and on j only,
-//     never on the motion state;
-//   * the Newton/Euler equations + velocity update (dyn) need the coefficients and (v, w);
-//   * the Euler angles / world position / body-frame integrals (kin) only consume (v, w) and never
-//     feed back (there is no gravity or current in the reference's model).
-//
-// So one block of three warps owns 32 envs: warp 2 produces coefficient sets ahead of time, warp 0
-// runs the ~85-instruction dyn recurrence (the true critical path), warp 1 integrates the
-// kinematics behind it.  The stages talk through two shared-memory rings, indexed by substep,
-// with chunk-granular (16 substeps) double-buffered hand-off on named barriers
-// (bar.arrive on the producer side, bar.sync on the consumer side), so the critical warp never
-// waits unless a producer has fallen a full chunk behind.  Each warp sits on its own SM
-// sub-partition (warp id % 4).  Results equal the fused kernel's up to the grouping of the fp32
-// chunk sums (tests/test_gpu_parity.py::test_pipeline_kernel_matches_fused_kernel).
+// and the step time is K_max (~1340 substeps of the slowest env) x the time ONE warp needs per
+// substep -- and that warp is bound by instruction issue: 365 instructions per substep while the
+// body shape moves (kinematics + dynamics + the fp64 shape chain and its ~100-instruction
+// coefficient set), 166 afterwards.  But the shape and every coefficient derived from it depend on
+// the action and the substep index only, never on the motion state.  So one block of TWO warps
+// owns 32 envs:
+//   * warp 1 (producer) runs the shape updates j = 1..W ahead of time and publishes each
+//     coefficient set in a shared-memory ring (slot j % 32, 28 floats per lane, 128-bit accesses);
+//   * warp 0 (consumer) runs the same software-pipelined kin(k-1) || dyn(k) loop as the fused
+//     kernel, loading its coefficients from the ring instead of computing them.
+// Each warp sits on its own SM sub-partition.  Hand-off is chunk-granular (8 substeps, 4 chunks in
+// flight) on named barriers: bar.arrive on the side that is done with a chunk, bar.sync on the
+// side that needs it, so neither warp waits unless the other has fallen a whole chunk behind.
+// The two warps execute exactly the arithmetic of run_cycle_mixed (same functions, same fixed
+// 32-substep grouping of the fp32 chunk sums): results are bit-identical with the fused kernel
+// (tests/test_gpu_parity.py::test_pipeline_kernel_matches_fused_kernel).
 #pragma once
 #include "salp_env.cuh"
 
-#define SALP_PIPE_CHUNK 16
-#define SALP_PIPE_SLOTS (2 * SALP_PIPE_CHUNK)
-#define SALP_PIPE_NCOEF 26
-#define SALP_PIPE_THREADS 96
+#define SALP_PIPE_CHUNK 8
+#define SALP_PIPE_NBUF 4
+#define SALP_PIPE_SLOTS (SALP_PIPE_CHUNK * SALP_PIPE_NBUF)
+#define SALP_PIPE_NCOEF 28
+#define SALP_PIPE_THREADS 64
 
 struct PipeShared {
-  float ringA[SALP_PIPE_SLOTS][SALP_PIPE_NCOEF][32];   // shape -> dyn : Coef32 of substep j, slot j % SLOTS
-  float ringB[SALP_PIPE_SLOTS][6][32];                 // dyn -> kin   : (v, w) after substep j
-  double merge[22][32];                                // kin / shape results for the epilogue (warp 0)
+  float ring[SALP_PIPE_SLOTS][32][SALP_PIPE_NCOEF];     // Coef32 of substep j in slot j % SLOTS, one 112-byte row per lane
+  double merge[9][32];                                  // the producer's final shape state, for the consumer's epilogue
 };
+static inline size_t pipe_smem_bytes(const SalpParams& p) {
+  return sizeof(PipeShared) + sizeof(float) * 2 * 32 * (SALP_OBS_BASE + 2 * p.num_obstacles);
+}
 
 __device__ __forceinline__ void pipe_bar_sync(int id) {
   asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
 }
 __device__ __forceinline__ void pipe_bar_arrive(int id) {
+  __threadfence_block();
   asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory");
 }
-// named barriers (0 is __syncthreads): full/empty x double buffer, for both rings
-#define PIPE_FULL_A(b) (1 + (b))
-#define PIPE_EMPTY_A(b) (3 + (b))
-#define PIPE_FULL_B(b) (5 + (b))
-#define PIPE_EMPTY_B(b) (7 + (b))
+// named barriers (0 is __syncthreads)
+#define PIPE_FULL(b) (1 + (b))
+#define PIPE_EMPTY(b) (1 + SALP_PIPE_NBUF + (b))
 
-__device__ __forceinline__ void coef_store(const Coef32& g, float (*slot)[32], int lane) {
-  int f = 0;
-#pragma unroll
-  for (int i = 0; i < 3; i++) slot[f++][lane] = g.aj[i];
-#pragma unroll
-  for (int i = 0; i < 3; i++) slot[f++][lane] = g.kdm[i];
-#pragma unroll
-  for (int i = 0; i < 3; i++) slot[f++][lane] = g.mrm[i];
-  slot[f++][lane] = g.com; slot[f++][lane] = g.com_rate; slot[f++][lane] = g.com_acc;
-  slot[f++][lane] = g.tj1; slot[f++][lane] = g.tj2;
-#pragma unroll
-  for (int i = 0; i < 3; i++) slot[f++][lane] = g.kqI[i];
-#pragma unroll
-  for (int i = 0; i < 3; i++) slot[f++][lane] = g.klI[i];
-#pragma unroll
-  for (int i = 0; i < 3; i++) slot[f++][lane] = g.JdI[i];
-#pragma unroll
-  for (int i = 0; i < 3; i++) slot[f++][lane] = g.AdI[i];
+__device__ __forceinline__ void coef_store(const Coef32& g, float* row) {
+  float4* q = reinterpret_cast<float4*>(row);
+  q[0] = make_float4(g.aj[0], g.aj[1], g.aj[2], g.kdm[0]);
+  q[1] = make_float4(g.kdm[1], g.kdm[2], g.mrm[0], g.mrm[1]);
+  q[2] = make_float4(g.mrm[2], g.com, g.com_rate, g.com_acc);
+  q[3] = make_float4(g.tj1, g.tj2, g.kqI[0], g.kqI[1]);
+  q[4] = make_float4(g.kqI[2], g.klI[0], g.klI[1], g.klI[2]);
+  q[5] = make_float4(g.JdI[0], g.JdI[1], g.JdI[2], g.AdI[0]);
+  q[6] = make_float4(g.AdI[1], g.AdI[2], 0.f, 0.f);
 }
-__device__ __forceinline__ void coef_load(Coef32& g, const float (*slot)[32], int lane) {
-  int f = 0;
-#pragma unroll
-  for (int i = 0; i < 3; i++) g.aj[i] = slot[f++][lane];
-#pragma unroll
-  for (int i = 0; i < 3; i++) g.kdm[i] = slot[f++][lane];
-#pragma unroll
-  for (int i = 0; i < 3; i++) g.mrm[i] = slot[f++][lane];
-  g.com = slot[f++][lane]; g.com_rate = slot[f++][lane]; g.com_acc = slot[f++][lane];
-  g.tj1 = slot[f++][lane]; g.tj2 = slot[f++][lane];
-#pragma unroll
-  for (int i = 0; i < 3; i++) g.kqI[i] = slot[f++][lane];
-#pragma unroll
-  for (int i = 0; i < 3; i++) g.klI[i] = slot[f++][lane];
-#pragma unroll
-  for (int i = 0; i < 3; i++) g.JdI[i] = slot[f++][lane];
-#pragma unroll
-  for (int i = 0; i < 3; i++) g.AdI[i] = slot[f++][lane];
+__device__ __forceinline__ void coef_load(Coef32& g, const float* row) {
+  const float4* q = reinterpret_cast<const float4*>(row);
+  float4 a = q[0], b = q[1], c = q[2], d = q[3], e = q[4], f = q[5], h = q[6];
+  g.aj[0] = a.x; g.aj[1] = a.y; g.aj[2] = a.z; g.kdm[0] = a.w;
+  g.kdm[1] = b.x; g.kdm[2] = b.y; g.mrm[0] = b.z; g.mrm[1] = b.w;
+  g.mrm[2] = c.x; g.com = c.y; g.com_rate = c.z; g.com_acc = c.w;
+  g.tj1 = d.x; g.tj2 = d.y; g.kqI[0] = d.z; g.kqI[1] = d.w;
+  g.kqI[2] = e.x; g.klI[0] = e.y; g.klI[1] = e.z; g.klI[2] = e.w;
+  g.JdI[0] = f.x; g.JdI[1] = f.y; g.JdI[2] = f.z; g.AdI[0] = f.w;
+  g.AdI[1] = h.x; g.AdI[2] = h.y;
 }
 
 __global__ void __launch_bounds__(SALP_PIPE_THREADS, 1)
@@ -91,13 +72,14 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
                       const __grid_constant__ SalpView v, const __grid_constant__ SalpStepIO io, uint32_t flags) {
   extern __shared__ __align__(16) unsigned char pipe_smem[];
   PipeShared& sh = *reinterpret_cast<PipeShared*>(pipe_smem);
+  float* tile = reinterpret_cast<float*>(pipe_smem + sizeof(PipeShared));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t i = (int64_t)blockIdx.x * 32 + lane;
   const bool live = i < v.n;
   constexpr int C = SALP_PIPE_CHUNK;
 
-  // Every warp reads the env's action and state itself (reads only; all writes happen in warp 0's
-  // epilogue after the block-wide barrier) and derives the same integer plan.
+  // Both warps read the env's action and state themselves (reads only; every write happens in the
+  // consumer's epilogue after the block-wide barrier) and derive the same integer plan.
   StepCtx cx;
   Body64 b;
   int Kraw = 0;
@@ -109,111 +91,112 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
     if (Kraw > 0) pp = make_phase_plan(cx.plan, v.time_table, dv.inv_dt);
   }
   const int K = Kraw > 0 ? Kraw : 0;
+  // body-frame integrals at the START of the cycle (env_step_end stores them as prev_position / prev_angle)
+  const double pos0[3] = {b.pos[0], b.pos[1], b.pos[2]};
+  const double ang0[3] = {b.ang[0], b.ang[1], b.ang[2]};
+  // the same warp-uniform end of the shape-update part as run_cycle_mixed (updates j = 1..min(W, K))
+  const int lane_end = pp.upd_a_end > pp.upd_b_end ? pp.upd_a_end : pp.upd_b_end;
+  const int W = __reduce_max_sync(0xffffffffu, K > 0 ? (lane_end < K ? lane_end : K) : 0);
   const int Kw = __reduce_max_sync(0xffffffffu, K);
-  const int nchunks = Kw / C + 1;                          // chunks of update/substep indices j = 0..Kw
+  const int kA = W < K ? W : K;
+  const int Wmax = W < Kw ? W : Kw;
+  const int nch = (Wmax + C - 1) / C;
+  const float dir[3] = {(float)cx.plan.dir[0], (float)cx.plan.dir[1], (float)cx.plan.dir[2]};
 
-  if (warp == 2) {
-    // ---------------- shape warp: coefficient sets, ahead of the dyn warp ----------------
+  if (warp == 1) {
+    // ---------------- producer: coefficient sets g_j, j = 1..kA ----------------
     ShapeTrack st;
     Coef32 g;
-    const float dir[3] = {(float)cx.plan.dir[0], (float)cx.plan.dir[1], (float)cx.plan.dir[2]};
-    int next_upd = 0x7fffffff;
-    if (K > 0) {
-      mixed_init_shape(p, dv, b, dir, st, g);
-      next_upd = 0;
-    }
-    for (int c = 0; c < nchunks; c++) {
-      const int bsel = c & 1;
-      if (c >= 2) pipe_bar_sync(PIPE_EMPTY_A(bsel));
-      const int jend = (c * C + C - 1 < Kw) ? c * C + C - 1 : Kw;
-      for (int j = c * C; j <= jend; j++) {
-        if (j == next_upd && j <= K) {
-          if (j > 0) shape_update(p, dv, cx.plan, v.time_table, dir, j, pp.k_T0, pp.k_jet, st, g);
-          if (j < K) coef_store(g, sh.ringA[j % SALP_PIPE_SLOTS], lane);
-          next_upd = j == 0 ? 1 : next_update_after(j, pp);
+    if (K > 0) mixed_init_shape(p, dv, b, dir, st, g);
+    double tj = v.time_table[1];                   // carried by the same additions as the table (robot.py:674)
+    int j = 1;
+    for (int c = 0; c < nch; c++) {
+      if (c >= SALP_PIPE_NBUF) pipe_bar_sync(PIPE_EMPTY(c % SALP_PIPE_NBUF));
+      const int je = (c + 1) * C < Wmax ? (c + 1) * C : Wmax;
+      for (; j <= je; j++) {
+        if (j <= kA) {
+          shape_update_at(p, dv, cx.plan, tj, dir, j, pp.k_T0, pp.k_jet, st, g);
+          coef_store(g, &sh.ring[j % SALP_PIPE_SLOTS][lane][0]);
         }
+        tj = rn::dadd(tj, p.dt);
       }
-      pipe_bar_arrive(PIPE_FULL_A(bsel));
+      __syncwarp();
+      pipe_bar_arrive(PIPE_FULL(c % SALP_PIPE_NBUF));
     }
-    if (K > 0) mixed_finish_shape(p, st, K, b);
-    sh.merge[13][lane] = b.length; sh.merge[14][lane] = b.width; sh.merge[15][lane] = b.prev_volume;
-    sh.merge[16][lane] = b.prevI[0]; sh.merge[17][lane] = b.prevI[1];
-    sh.merge[18][lane] = b.com; sh.merge[19][lane] = b.com_rate; sh.merge[20][lane] = b.prev_com_rate;
-    sh.merge[21][lane] = b.com_acc;
-  } else if (warp == 0) {
-    // ---------------- dyn warp: the critical recurrence ----------------
+    if (K > 0) {
+      mixed_finish_shape(p, st, K, b);
+      sh.merge[0][lane] = b.length; sh.merge[1][lane] = b.width; sh.merge[2][lane] = b.prev_volume;
+      sh.merge[3][lane] = b.prevI[0]; sh.merge[4][lane] = b.prevI[1];
+      sh.merge[5][lane] = b.com; sh.merge[6][lane] = b.com_rate; sh.merge[7][lane] = b.prev_com_rate;
+      sh.merge[8][lane] = b.com_acc;
+    }
+  } else {
+    // ---------------- consumer: kin(k-1) || dyn(k), coefficients from the ring ----------------
     Motion32 s;
     Coef32 g;
-    mixed_init_dyn(b, s);
-    int next_upd = 0;
-    for (int c = 0; c < nchunks; c++) {
-      const int bsel = c & 1;
-      pipe_bar_sync(PIPE_FULL_A(bsel));
-      if (c >= 2) pipe_bar_sync(PIPE_EMPTY_B(bsel));
-      const int jend = (c * C + C - 1 < Kw) ? c * C + C - 1 : Kw;
-      for (int j = c * C; j <= jend; j++) {
-        if (j < K) {
-          if (j == next_upd) {
-            coef_load(g, sh.ringA[j % SALP_PIPE_SLOTS], lane);
-            next_upd = j == 0 ? 1 : next_update_after(j, pp);
-          }
-          dyn_step(dv, g, s);
-          float(*slot)[32] = sh.ringB[j % SALP_PIPE_SLOTS];
-          slot[0][lane] = s.v0; slot[1][lane] = s.v1; slot[2][lane] = s.v2;
-          slot[3][lane] = s.w0; slot[4][lane] = s.w1; slot[5][lane] = s.w2;
-        }
-      }
-      pipe_bar_arrive(PIPE_EMPTY_A(bsel));
-      pipe_bar_arrive(PIPE_FULL_B(bsel));
+    if (K > 0) {
+      ShapeTrack st0;
+      mixed_init_shape(p, dv, b, dir, st0, g);      // g_0 (once; cheaper than a hand-off)
+      mixed_init_dyn(b, s);
+      mixed_init_kin(b, s);
+      dyn_step(dv, g, s);
     }
-    if (K > 0) mixed_finish_dyn(s, b);
-  } else {
-    // ---------------- kin warp: Euler angles, world position, body-frame integrals ----------------
-    Motion32 s;
-    mixed_init_kin(b, s);
-    for (int c = 0; c < nchunks; c++) {
-      const int bsel = c & 1;
-      pipe_bar_sync(PIPE_FULL_B(bsel));
-      const int jend = (c * C + C - 1 < Kw) ? c * C + C - 1 : Kw;
-      for (int j = c * C; j <= jend; j++) {
-        if (j < K) {
-          const float(*slot)[32] = sh.ringB[j % SALP_PIPE_SLOTS];
-          s.v0 = slot[0][lane]; s.v1 = slot[1][lane]; s.v2 = slot[2][lane];
-          s.w0 = slot[3][lane]; s.w1 = slot[4][lane]; s.w2 = slot[5][lane];
+    int kk = 1;
+    const int WA = Wmax < Kw - 1 ? Wmax : Kw - 1;   // iterations kk = 1..K-1 exist; those <= W load g_kk
+    for (int c = 0; c < nch; c++) {
+      pipe_bar_sync(PIPE_FULL(c % SALP_PIPE_NBUF));
+      const int ce = (c + 1) * C < WA ? (c + 1) * C : WA;
+      for (; kk <= ce; kk++) {
+        if (kk < K) {
+          coef_load(g, &sh.ring[kk % SALP_PIPE_SLOTS][lane][0]);
           kin_step(dv, s);
+          dyn_step(dv, g, s);
+          if ((kk & (SALP_MIXED_CHUNK - 1)) == 0) flush_chunk(b, s);
         }
       }
-      if (c * C < K) flush_chunk(b, s);
-      pipe_bar_arrive(PIPE_EMPTY_B(bsel));
+      __syncwarp();
+      pipe_bar_arrive(PIPE_EMPTY(c % SALP_PIPE_NBUF));
     }
-    if (K > 0) b.speed_world = (double)sqrtf(s.vw0 * s.vw0 + s.vw1 * s.vw1);
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      sh.merge[k][lane] = b.pw[k]; sh.merge[3 + k][lane] = b.pos[k];
-      sh.merge[6 + k][lane] = b.ang[k]; sh.merge[9 + k][lane] = b.eul[k];
+    // the coast: the fused kernel's lean loop, same fixed chunk boundaries
+    int k = kk;
+    while (k < K) {
+      const int boundary = ((k - 1) & ~(SALP_MIXED_CHUNK - 1)) + SALP_MIXED_CHUNK + 1;
+      const int cend = boundary < K ? boundary : K;
+      for (; k < cend; k++) {
+        kin_step(dv, s);
+        dyn_step(dv, g, s);
+      }
+      if (k == boundary) flush_chunk(b, s);
     }
-    sh.merge[12][lane] = b.speed_world;
+    if (K > 0) {
+      kin_step(dv, s);
+      flush_chunk(b, s);
+      mixed_finish_dyn(s, b);
+      b.speed_world = (double)sqrtf(s.vw0 * s.vw0 + s.vw1 * s.vw1);
+    }
   }
   __syncthreads();
-  if (warp == 0 && live) {
-    const double pos0[3] = {b.pos[0], b.pos[1], b.pos[2]};
-    const double ang0[3] = {b.ang[0], b.ang[1], b.ang[2]};
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      b.pw[k] = sh.merge[k][lane]; b.pos[k] = sh.merge[3 + k][lane];
-      b.ang[k] = sh.merge[6 + k][lane]; b.eul[k] = sh.merge[9 + k][lane];
-    }
-    b.speed_world = sh.merge[12][lane];
-    b.length = sh.merge[13][lane]; b.width = sh.merge[14][lane]; b.prev_volume = sh.merge[15][lane];
-    b.prevI[0] = sh.merge[16][lane]; b.prevI[1] = sh.merge[17][lane]; b.prevI[2] = K > 0 ? sh.merge[17][lane] : b.prevI[2];
-    b.com = sh.merge[18][lane]; b.com_rate = sh.merge[19][lane]; b.prev_com_rate = sh.merge[20][lane];
-    b.com_acc = sh.merge[21][lane];
+  if (warp != 0) return;
+  if (live) {
     double t = 0.0;
     if (K > 0) {
-      b.prev_com = b.com;
+      b.length = sh.merge[0][lane]; b.width = sh.merge[1][lane]; b.prev_volume = sh.merge[2][lane];
+      b.prevI[0] = sh.merge[3][lane]; b.prevI[1] = sh.merge[4][lane]; b.prevI[2] = sh.merge[4][lane];
+      b.com = sh.merge[5][lane]; b.prev_com = sh.merge[5][lane]; b.com_rate = sh.merge[6][lane];
+      b.prev_com_rate = sh.merge[7][lane]; b.com_acc = sh.merge[8][lane];
       t = v.time_table[K];
       b.phase = phase_at(cx.plan, t);
     }
-    env_step_end(p, v, io, flags, i, cx, pos0, ang0, b, Kraw, t);
+    env_step_end(p, v, io, flags, i, cx, pos0, ang0, b, Kraw, t, tile + lane * (SALP_OBS_BASE + 2 * p.num_obstacles),
+                 io.terminal_obs ? tile + (32 + lane) * (SALP_OBS_BASE + 2 * p.num_obstacles) : nullptr);
+  }
+  __syncwarp();
+  const int D = SALP_OBS_BASE + 2 * p.num_obstacles;
+  const int rows = __popc(__ballot_sync(0xffffffffu, live));
+  for (int j = lane; j < 32 * D; j += 32) {
+    if (j < rows * D) {
+      io.obs[(int64_t)blockIdx.x * 32 * D + j] = tile[j];
+      if (io.terminal_obs) io.terminal_obs[(int64_t)blockIdx.x * 32 * D + j] = tile[32 * D + j];
+    }
   }
 }

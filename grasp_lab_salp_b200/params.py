@@ -22,6 +22,7 @@ PRECISION_MIXED = 1
 STEP_AUTORESET = 1
 STEP_SORT_BY_K = 2
 STEP_PIPELINE = 4
+STEP_FUSED = 8
 
 RAND_ACTION, RAND_OBSERVATION, RAND_DYNAMICS, RAND_DISTURBANCE, RAND_LATENCY = 1, 2, 4, 8, 16
 
