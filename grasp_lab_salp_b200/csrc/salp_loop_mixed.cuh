@@ -186,11 +186,21 @@ SALP_HD void shape64_at(const SalpParams& p, const SalpDerived& k, double lh, do
   I1 = (k.c2 * lh2 + k.c1 * lh + k.c0) + sw * (lh2 + wh2);
   com = (k.comA * lh + k.comB) / (k.mtot0 + wm);
 }
-// The same chain inside the substep loop: the division by the total mass D is replaced by three
-// Newton steps on the reciprocal carried from the previous update (D moves by < 5 % between
-// consecutive updates even next to the integrator's stability limit: (0.05)^8 ~ 4e-11, and
-// ~1e-22 for regular cycles), which takes a ~200-cycle DDIV off the loop's critical path.
-SALP_HD void shape64_step(const SalpParams& p, const SalpDerived& k, double lh, double wh, double& rD, double& Dprev,
+// The same chain inside the substep loop.  The division by the total mass D is a hardware
+// reciprocal seed (rcp.approx.ftz.f64, ~20 good bits) refined by two Newton steps (2^-20 -> 2^-40
+// -> below fp64 rounding): 5 dependent operations instead of a ~200-cycle DDIV, a pure function of
+// D (an unchanged shape reproduces every bit: redundant updates stay exact no-ops), and no value
+// carried from the previous update, so consecutive updates are independent chains.
+SALP_HD double rcp64_seed(double x) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return r;
+#else
+  return (double)(1.0f / (float)x);
+#endif
+}
+SALP_HD void shape64_step(const SalpParams& p, const SalpDerived& k, double lh, double wh,
                           double& V, double& I0, double& I1, double& com) {
   double wh2 = wh * wh, lh2 = lh * lh;
   double Ve = k.four_thirds_pi * lh * wh2;
@@ -199,13 +209,9 @@ SALP_HD void shape64_step(const SalpParams& p, const SalpDerived& k, double lh, 
   double sw = k.skin3 + 200.0 * Ve;
   I0 = sw * (wh2 + wh2);
   I1 = (k.c2 * lh2 + k.c1 * lh + k.c0) + sw * (lh2 + wh2);
-  double r = rD;
+  double r = rcp64_seed(D);
   r = r * (2.0 - D * r);
   r = r * (2.0 - D * r);
-  r = r * (2.0 - D * r);
-  r = (D == Dprev) ? rD : r;      // unchanged shape: keep the reciprocal bit for bit (the update is then an exact no-op)
-  rD = r;
-  Dprev = D;
   com = (k.comA * lh + k.comB) * r;
 }
 
@@ -396,7 +402,6 @@ SALP_HD void flush_chunk(Body64& b, Motion32& s) {
 struct ShapeTrack {
   Shape64 s;
   double prev_com_rate, com_acc, prevV, I0_prev_used, I1_prev_used, dl;
-  double rD, Dprev;             // carried reciprocal of the total mass and the mass it belongs to (shape64_step)
   int last_update;
 };
 
@@ -415,7 +420,7 @@ SALP_HD void shape_update_at(const SalpParams& p, const SalpDerived& dv, const C
   st.dl = shape_delta(phase, t, c.refill, c.T0, (double)c.contraction32, c.contract_rate, c.release_rate);
   double lh = 0.5 * (p.init_length - st.dl), wh = 0.5 * (p.init_width + st.dl);
   double V, I0n, I1n, com;
-  shape64_step(p, dv, lh, wh, st.rD, st.Dprev, V, I0n, I1n, com);
+  shape64_step(p, dv, lh, wh, V, I0n, I1n, com);
   double dV_dt = (V - st.s.V) * dv.inv_dt;
   double com_rate = (com - st.s.com) * dv.inv_dt;                // robot.py:901-910
   st.com_acc = (com_rate - st.prev_com_rate) * dv.inv_dt;        // robot.py:912-922
@@ -442,8 +447,6 @@ SALP_HD void mixed_init_shape(const SalpParams& p, const SalpDerived& dv, const 
   st.last_update = 0;
   double lh = 0.5 * b.length, wh = 0.5 * b.width, wm, com_now;
   shape64_at(p, dv, lh, wh, st.s.V, st.s.I0, st.s.I1, com_now, wm);
-  st.Dprev = dv.mtot0 + wm;
-  st.rD = 1.0 / st.Dprev;
   double dV_dt = (st.s.V - b.prev_volume) * dv.inv_dt;
   // the carried centre of mass may be stale w.r.t. length/width (Robot.reset quirk, robot.py:478)
   st.s.com = b.com;

@@ -113,12 +113,31 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
     for (int c = 0; c < nch; c++) {
       if (c >= SALP_PIPE_NBUF) pipe_bar_sync(PIPE_EMPTY(c % SALP_PIPE_NBUF));
       const int je = (c + 1) * C < Wmax ? (c + 1) * C : Wmax;
-      for (; j <= je; j++) {
-        if (j <= kA) {
-          shape_update_at(p, dv, cx.plan, tj, dir, j, pp.k_T0, pp.k_jet, st, g);
-          coef_store(g, &sh.ring[j % SALP_PIPE_SLOTS][lane][0]);
+      // two updates per trip: consecutive updates are independent chains until their backward
+      // differences (shape64_step carries nothing), so the scheduler overlaps them and the warp is
+      // bound by instruction issue instead of by the latency of one fp64 chain
+      while (j <= je) {
+        const double tj1 = rn::dadd(tj, p.dt);
+        if (j + 1 <= je) {
+          if (j + 1 <= kA) {
+            shape_update_at(p, dv, cx.plan, tj, dir, j, pp.k_T0, pp.k_jet, st, g);
+            coef_store(g, &sh.ring[j % SALP_PIPE_SLOTS][lane][0]);
+            shape_update_at(p, dv, cx.plan, tj1, dir, j + 1, pp.k_T0, pp.k_jet, st, g);
+            coef_store(g, &sh.ring[(j + 1) % SALP_PIPE_SLOTS][lane][0]);
+          } else if (j <= kA) {
+            shape_update_at(p, dv, cx.plan, tj, dir, j, pp.k_T0, pp.k_jet, st, g);
+            coef_store(g, &sh.ring[j % SALP_PIPE_SLOTS][lane][0]);
+          }
+          tj = rn::dadd(tj1, p.dt);
+          j += 2;
+        } else {
+          if (j <= kA) {
+            shape_update_at(p, dv, cx.plan, tj, dir, j, pp.k_T0, pp.k_jet, st, g);
+            coef_store(g, &sh.ring[j % SALP_PIPE_SLOTS][lane][0]);
+          }
+          tj = tj1;
+          j += 1;
         }
-        tj = rn::dadd(tj, p.dt);
       }
       __syncwarp();
       pipe_bar_arrive(PIPE_FULL(c % SALP_PIPE_NBUF));
