@@ -80,7 +80,7 @@ struct SalpDerived {
   // fp64 shape chain
   double inv_dt, four_thirds_pi, skin3, c2, c1, c0, comA, comB, mtot0, m0, jet_gain;
   // fp32
-  float dt, ratio_f, pi, end_aspect, inv_aspect_span, half_rho_neg, torque_ratio, arm0;
+  float dt, ratio_f, pi, end_aspect, inv_aspect_span, half_rho_neg, half_rho_pi, torque_ratio, arm0;
   float init_length_f, init_width_f, jet_gain_f, rho_f, m_base_f, four_thirds_pi_f, skin3_f, c2_f, c1_f, c0_f;   // fp32 shape (never differenced)
   float Ca[3], E[3], Cat[3], Car[3], CaD[3], CatF[3];
   float thi[3], tspan[3], rhi[3], rspan[3];
@@ -127,6 +127,7 @@ SALP_HD SalpDerived make_derived(const SalpParams& p) {
   k.end_aspect = (float)end_aspect;
   k.inv_aspect_span = (float)(1.0 / (init_aspect - end_aspect));
   k.half_rho_neg = (float)(-0.5 * p.density);
+  k.half_rho_pi = (float)(-0.5 * p.density * M_PI);
   k.torque_ratio = (float)p.drag_torque_ratio;
   k.arm0 = -(float)(p.nozzle_length1 + p.nozzle_length2);
   for (int i = 0; i < 3; i++) {
@@ -221,45 +222,50 @@ SALP_HD void shape64_step(const SalpParams& p, const SalpDerived& k, double lh, 
 SALP_HD void make_coefs(const SalpDerived& k, const float dir[3], bool jet_on, float lh, float wh,
                         float I_rate0, float I_rate1, float dV_dt, float com, float com_rate, float com_acc,
                         Coef32& g) {
-  const float wh2 = wh * wh, lh2 = lh * lh;
-  const float Ve = k.four_thirds_pi_f * lh * wh2;                  // geometry.py:79-81
+  // common sub-products are shared by hand (the compiler may not reassociate): ~85 instructions
+  const float wh2 = wh * wh, lh2 = lh * lh, lw = lh * wh;
+  const float Ve = k.four_thirds_pi_f * (lw * wh);                 // geometry.py:79-81
   const float m = fmaf(k.rho_f, Ve, k.m_base_f);                   // robot.py:1055-1063
   const float sw = fmaf(200.0f, Ve, k.skin3_f);                    // geometry.py:134-183
-  const float I0 = sw * (wh2 + wh2);
-  const float I1 = fmaf(k.c2_f, lh2, fmaf(k.c1_f, lh, k.c0_f)) + sw * (lh2 + wh2);
+  const float swh = sw * wh2;
+  const float I0 = swh + swh;
+  const float I1 = fmaf(sw, lh2 + wh2, fmaf(k.c2_f, lh2, fmaf(k.c1_f, lh, k.c0_f)));
   const float inv_m = fast_rcp(m);
   const float inv_I0 = fast_rcp(I0), inv_I1 = fast_rcp(I1);
-  const float a0 = k.pi * wh2, a1 = k.pi * lh * wh;                // geometry.py:68-75
-  float nr = (lh * fast_rcp(wh) - k.end_aspect) * k.inv_aspect_span;   // geometry.py:105-123
+  // aspect-ratio interpolation of the drag coefficients (geometry.py:105-123)
+  float nr = (lh * fast_rcp(wh) - k.end_aspect) * k.inv_aspect_span;
   nr = fminf(fmaxf(nr, 0.0f), 1.0f);
-  const float width = wh + wh;
-  const float w3 = width * width * width, l3 = 8.0f * lh * lh2;
-  const float area[3] = {a0, a1, a1};
-  const float dims[3] = {w3, l3, l3};
-  const float I[3] = {I0, I1, I1};
-  const float inv_I[3] = {inv_I0, inv_I1, inv_I1};
-  const float I_rate[3] = {I_rate0, I_rate1, I_rate1};
+  // -rho/2 * area_i (geometry.py:68-75: areas pi wh^2, pi lh wh, pi lh wh)
+  const float P0 = k.half_rho_pi * wh2, P1 = k.half_rho_pi * lw;
+  const float Q0 = P0 * inv_m, Q1 = P1 * inv_m;
+  const float ct0 = fmaf(-nr, k.tspan[0], k.thi[0]), ct1 = fmaf(-nr, k.tspan[1], k.thi[1]), ct2 = fmaf(-nr, k.tspan[2], k.thi[2]);
+  const float cr0 = fmaf(-nr, k.rspan[0], k.rhi[0]), cr1 = fmaf(-nr, k.rspan[1], k.rhi[1]), cr2 = fmaf(-nr, k.rspan[2], k.rhi[2]);
+  g.kdm[0] = Q0 * ct0; g.kdm[1] = Q1 * ct1; g.kdm[2] = Q1 * ct2;
+  const float mr = (k.rho_f * dV_dt) * inv_m;                      // mass_rate / m   (geometry.py:98-101)
+  g.mrm[0] = mr * k.Car[0]; g.mrm[1] = mr * k.Car[1]; g.mrm[2] = mr * k.Car[2];
   const float f = jet_on ? k.jet_gain_f * dV_dt * dV_dt : 0.0f;
-  const float mass_rate = k.rho_f * dV_dt;                         // geometry.py:98-101
-  const float armx = k.arm0 - lh;
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
-    float ct = k.thi[i] - nr * k.tspan[i];
-    float cr = k.rhi[i] - nr * k.rspan[i];
-    g.kdm[i] = k.half_rho_neg * area[i] * ct * inv_m;
-    g.mrm[i] = mass_rate * k.Car[i] * inv_m;
-    g.aj[i] = dir[i] * f * inv_m;
-    float kr = k.half_rho_neg * cr * area[i];
-    g.kqI[i] = kr * dims[i] * inv_I[i];
-    g.klI[i] = (k.torque_ratio * kr * width - I_rate[i]) * inv_I[i];
-    g.JdI[i] = (I[i2] * k.CatF[i2] - I[i1] * k.CatF[i1]) * inv_I[i];
-    g.AdI[i] = m * k.CaD[i] * inv_I[i];
-  }
+  const float fm = f * inv_m;
+  g.aj[0] = dir[0] * fm; g.aj[1] = dir[1] * fm; g.aj[2] = dir[2] * fm;
+  const float kr0 = P0 * cr0, kr1 = P1 * cr1, kr2 = P1 * cr2;
+  // drag torque: dims = (width^3, length^3, length^3) = 8 (wh^3, lh^3, lh^3)
+  const float E0 = (wh2 * wh) * (8.0f * inv_I0), E1 = (lh2 * lh) * (8.0f * inv_I1);
+  g.kqI[0] = kr0 * E0; g.kqI[1] = kr1 * E1; g.kqI[2] = kr2 * E1;
+  const float tw = k.torque_ratio * (wh + wh);
+  g.klI[0] = fmaf(kr0, tw, -I_rate0) * inv_I0;
+  g.klI[1] = fmaf(kr1, tw, -I_rate1) * inv_I1;
+  g.klI[2] = fmaf(kr2, tw, -I_rate1) * inv_I1;
+  // (J_i2 - J_i1) / I_i with J = I o (1 + Cat), I = (I0, I1, I1)
+  const float r01 = I0 * inv_I1;
+  g.JdI[0] = (I1 * inv_I0) * (k.CatF[2] - k.CatF[1]);
+  g.JdI[1] = fmaf(r01, k.CatF[0], -k.CatF[2]);
+  g.JdI[2] = fmaf(-r01, k.CatF[0], k.CatF[1]);
+  const float mI0 = m * inv_I0, mI1 = m * inv_I1;
+  g.AdI[0] = mI0 * k.CaD[0]; g.AdI[1] = mI1 * k.CaD[1]; g.AdI[2] = mI1 * k.CaD[2];
   g.inv_m = inv_m;
   g.inv_Iz = inv_I1;
-  g.tj1 = -armx * (dir[2] * f) * inv_I1;
-  g.tj2 = armx * (dir[1] * f) * inv_I1;
+  const float afI = (k.arm0 - lh) * (f * inv_I1);                  // arm = (arm0 - lh, 0, 0)   robot.py:931-935
+  g.tj1 = -afI * dir[2];
+  g.tj2 = afI * dir[1];
   g.com = com;
   g.com_rate = com_rate;
   g.com_acc = com_acc;
