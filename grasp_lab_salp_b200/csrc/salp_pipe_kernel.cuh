@@ -25,6 +25,9 @@
 #define SALP_PIPE_SLOTS (SALP_PIPE_CHUNK * SALP_PIPE_NBUF)
 #define SALP_PIPE_NCOEF 28
 #define SALP_PIPE_THREADS 64
+#ifndef SALP_PIPE_UNROLL
+#define SALP_PIPE_UNROLL 4
+#endif
 
 struct PipeShared {
   float ring[SALP_PIPE_SLOTS][32][SALP_PIPE_NCOEF];     // Coef32 of substep j in slot j % SLOTS, one 112-byte row per lane
@@ -113,29 +116,24 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
     for (int c = 0; c < nch; c++) {
       if (c >= SALP_PIPE_NBUF) pipe_bar_sync(PIPE_EMPTY(c % SALP_PIPE_NBUF));
       const int je = (c + 1) * C < Wmax ? (c + 1) * C : Wmax;
-      // two updates per trip: consecutive updates are independent chains until their backward
-      // differences (shape64_step carries nothing), so the scheduler overlaps them and the warp is
-      // bound by instruction issue instead of by the latency of one fp64 chain
+      // SALP_PIPE_UNROLL updates per trip: consecutive updates are independent chains until their
+      // backward differences (shape64_step carries nothing), so the scheduler overlaps them and the
+      // warp is bound by instruction issue instead of by the latency of one fp64 chain
       while (j <= je) {
-        const double tj1 = rn::dadd(tj, p.dt);
-        if (j + 1 <= je) {
-          if (j + 1 <= kA) {
-            shape_update_at(p, dv, cx.plan, tj, dir, j, pp.k_T0, pp.k_jet, st, g);
-            coef_store(g, &sh.ring[j % SALP_PIPE_SLOTS][lane][0]);
-            shape_update_at(p, dv, cx.plan, tj1, dir, j + 1, pp.k_T0, pp.k_jet, st, g);
-            coef_store(g, &sh.ring[(j + 1) % SALP_PIPE_SLOTS][lane][0]);
-          } else if (j <= kA) {
-            shape_update_at(p, dv, cx.plan, tj, dir, j, pp.k_T0, pp.k_jet, st, g);
-            coef_store(g, &sh.ring[j % SALP_PIPE_SLOTS][lane][0]);
+        if (j + SALP_PIPE_UNROLL - 1 <= je && j + SALP_PIPE_UNROLL - 1 <= kA) {
+#pragma unroll
+          for (int u = 0; u < SALP_PIPE_UNROLL; u++) {
+            shape_update_at(p, dv, cx.plan, tj, dir, j + u, pp.k_T0, pp.k_jet, st, g);
+            coef_store(g, &sh.ring[(j + u) % SALP_PIPE_SLOTS][lane][0]);
+            tj = rn::dadd(tj, p.dt);
           }
-          tj = rn::dadd(tj1, p.dt);
-          j += 2;
+          j += SALP_PIPE_UNROLL;
         } else {
           if (j <= kA) {
             shape_update_at(p, dv, cx.plan, tj, dir, j, pp.k_T0, pp.k_jet, st, g);
             coef_store(g, &sh.ring[j % SALP_PIPE_SLOTS][lane][0]);
           }
-          tj = tj1;
+          tj = rn::dadd(tj, p.dt);
           j += 1;
         }
       }
