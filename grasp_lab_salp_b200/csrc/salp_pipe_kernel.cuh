@@ -119,23 +119,27 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
       // SALP_PIPE_UNROLL updates per trip: consecutive updates are independent chains until their
       // backward differences (shape64_step carries nothing), so the scheduler overlaps them and the
       // warp is bound by instruction issue instead of by the latency of one fp64 chain
+      // (j, tj and the trip structure stay warp-uniform; only the work inside is per lane)
       while (j <= je) {
-        if (j + SALP_PIPE_UNROLL - 1 <= je && j + SALP_PIPE_UNROLL - 1 <= kA) {
+        const int nu = je - j + 1 < SALP_PIPE_UNROLL ? je - j + 1 : SALP_PIPE_UNROLL;
+        if (nu == SALP_PIPE_UNROLL && j + SALP_PIPE_UNROLL - 1 <= kA) {
+          double tu = tj;
 #pragma unroll
           for (int u = 0; u < SALP_PIPE_UNROLL; u++) {
-            shape_update_at(p, dv, cx.plan, tj, dir, j + u, pp.k_T0, pp.k_jet, st, g);
+            shape_update_at(p, dv, cx.plan, tu, dir, j + u, pp.k_T0, pp.k_jet, st, g);
             coef_store(g, &sh.ring[(j + u) % SALP_PIPE_SLOTS][lane][0]);
-            tj = rn::dadd(tj, p.dt);
+            tu = rn::dadd(tu, p.dt);
           }
-          j += SALP_PIPE_UNROLL;
-        } else {
-          if (j <= kA) {
-            shape_update_at(p, dv, cx.plan, tj, dir, j, pp.k_T0, pp.k_jet, st, g);
-            coef_store(g, &sh.ring[j % SALP_PIPE_SLOTS][lane][0]);
+        } else if (j <= kA) {
+          double tu = tj;
+          for (int u = 0; u < nu && j + u <= kA; u++) {
+            shape_update_at(p, dv, cx.plan, tu, dir, j + u, pp.k_T0, pp.k_jet, st, g);
+            coef_store(g, &sh.ring[(j + u) % SALP_PIPE_SLOTS][lane][0]);
+            tu = rn::dadd(tu, p.dt);
           }
-          tj = rn::dadd(tj, p.dt);
-          j += 1;
         }
+        for (int u = 0; u < nu; u++) tj = rn::dadd(tj, p.dt);
+        j += nu;
       }
       __syncwarp();
       pipe_bar_arrive(PIPE_FULL(c % SALP_PIPE_NBUF));
