@@ -25,9 +25,6 @@
 #define SALP_PIPE_SLOTS (SALP_PIPE_CHUNK * SALP_PIPE_NBUF)
 #define SALP_PIPE_NCOEF 28
 #define SALP_PIPE_THREADS 64
-#ifndef SALP_PIPE_UNROLL
-#define SALP_PIPE_UNROLL 4
-#endif
 
 struct PipeShared {
   float ring[SALP_PIPE_SLOTS][32][SALP_PIPE_NCOEF];     // Coef32 of substep j in slot j % SLOTS, one 112-byte row per lane
@@ -116,30 +113,31 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
     for (int c = 0; c < nch; c++) {
       if (c >= SALP_PIPE_NBUF) pipe_bar_sync(PIPE_EMPTY(c % SALP_PIPE_NBUF));
       const int je = (c + 1) * C < Wmax ? (c + 1) * C : Wmax;
-      // SALP_PIPE_UNROLL updates per trip: consecutive updates are independent chains until their
-      // backward differences (shape64_step carries nothing), so the scheduler overlaps them and the
-      // warp is bound by instruction issue instead of by the latency of one fp64 chain
-      // (j, tj and the trip structure stay warp-uniform; only the work inside is per lane)
+      // two updates per trip: consecutive updates are independent chains until their backward
+      // differences (shape64_step carries nothing), so the scheduler overlaps them and the warp is
+      // bound by instruction issue instead of by the latency of one fp64 chain
       while (j <= je) {
-        const int nu = je - j + 1 < SALP_PIPE_UNROLL ? je - j + 1 : SALP_PIPE_UNROLL;
-        if (nu == SALP_PIPE_UNROLL && j + SALP_PIPE_UNROLL - 1 <= kA) {
-          double tu = tj;
-#pragma unroll
-          for (int u = 0; u < SALP_PIPE_UNROLL; u++) {
-            shape_update_at(p, dv, cx.plan, tu, dir, j + u, pp.k_T0, pp.k_jet, st, g);
-            coef_store(g, &sh.ring[(j + u) % SALP_PIPE_SLOTS][lane][0]);
-            tu = rn::dadd(tu, p.dt);
+        const double tj1 = rn::dadd(tj, p.dt);
+        if (j + 1 <= je) {
+          if (j + 1 <= kA) {
+            shape_update_at(p, dv, cx.plan, tj, dir, j, pp.k_T0, pp.k_jet, st, g);
+            coef_store(g, &sh.ring[j % SALP_PIPE_SLOTS][lane][0]);
+            shape_update_at(p, dv, cx.plan, tj1, dir, j + 1, pp.k_T0, pp.k_jet, st, g);
+            coef_store(g, &sh.ring[(j + 1) % SALP_PIPE_SLOTS][lane][0]);
+          } else if (j <= kA) {
+            shape_update_at(p, dv, cx.plan, tj, dir, j, pp.k_T0, pp.k_jet, st, g);
+            coef_store(g, &sh.ring[j % SALP_PIPE_SLOTS][lane][0]);
           }
-        } else if (j <= kA) {
-          double tu = tj;
-          for (int u = 0; u < nu && j + u <= kA; u++) {
-            shape_update_at(p, dv, cx.plan, tu, dir, j + u, pp.k_T0, pp.k_jet, st, g);
-            coef_store(g, &sh.ring[(j + u) % SALP_PIPE_SLOTS][lane][0]);
-            tu = rn::dadd(tu, p.dt);
+          tj = rn::dadd(tj1, p.dt);
+          j += 2;
+        } else {
+          if (j <= kA) {
+            shape_update_at(p, dv, cx.plan, tj, dir, j, pp.k_T0, pp.k_jet, st, g);
+            coef_store(g, &sh.ring[j % SALP_PIPE_SLOTS][lane][0]);
           }
+          tj = tj1;
+          j += 1;
         }
-        for (int u = 0; u < nu; u++) tj = rn::dadd(tj, p.dt);
-        j += nu;
       }
       __syncwarp();
       pipe_bar_arrive(PIPE_FULL(c % SALP_PIPE_NBUF));
