@@ -419,9 +419,19 @@ SALP_HD void shape_update(const SalpParams& p, const SalpDerived& dv, const Cycl
                           const float dir[3], int j, int k_T0, int k_jet, ShapeTrack& st, Coef32& g) {
   shape_update_at(p, dv, c, time_table[j], dir, j, k_T0, k_jet, st, g);
 }
+// The update in two stages, so that the pipeline kernel can run them on different warps:
+//   shape_front : fp64 -- shape at t_j, the differenced quantities, rounded to fp32 once  (ShapeFront)
+//   make_coefs  : fp32 -- the coefficient set from a ShapeFront (stateless)
+struct ShapeFront {
+  float dl;                       // init_length - length
+  float I_rate0, I_rate1;         // (I - I_prev) / dt                     robot.py:887-896
+  float dV_dt;                    // (V - V_prev) / dt
+  float com, com_rate, com_acc;   // robot.py:898-922
+  float jet_on;                   // 1 while the previous substep's state was JET (robot.py:937-951)
+};
 // t = t_j, the j-fold repeated `cycle_time += dt` (callers either read the table or carry the sum)
-SALP_HD void shape_update_at(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c, double t,
-                             const float dir[3], int j, int k_T0, int k_jet, ShapeTrack& st, Coef32& g) {
+SALP_HD void shape_front(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c, double t, int j, int k_T0,
+                         int k_jet, ShapeTrack& st, ShapeFront& f) {
   const int phase = j < k_T0 ? 0 : (j < k_jet ? 1 : 2);
   st.dl = shape_delta(phase, t, c.refill, c.T0, (double)c.contraction32, c.contract_rate, c.release_rate);
   double lh = 0.5 * (p.init_length - st.dl), wh = 0.5 * (p.init_width + st.dl);
@@ -431,15 +441,29 @@ SALP_HD void shape_update_at(const SalpParams& p, const SalpDerived& dv, const C
   double com_rate = (com - st.s.com) * dv.inv_dt;                // robot.py:901-910
   st.com_acc = (com_rate - st.prev_com_rate) * dv.inv_dt;        // robot.py:912-922
   st.prev_com_rate = com_rate;
-  const float dl32 = (float)st.dl;
-  make_coefs(dv, dir, phase == 1, 0.5f * (dv.init_length_f - dl32), 0.5f * (dv.init_width_f + dl32),
-             (float)((I0n - st.s.I0) * dv.inv_dt), (float)((I1n - st.s.I1) * dv.inv_dt),
-             (float)dV_dt, (float)com, (float)com_rate, (float)st.com_acc, g);
+  f.dl = (float)st.dl;
+  f.I_rate0 = (float)((I0n - st.s.I0) * dv.inv_dt);
+  f.I_rate1 = (float)((I1n - st.s.I1) * dv.inv_dt);
+  f.dV_dt = (float)dV_dt;
+  f.com = (float)com;
+  f.com_rate = (float)com_rate;
+  f.com_acc = (float)st.com_acc;
+  f.jet_on = phase == 1 ? 1.0f : 0.0f;
   st.prevV = st.s.V;
   st.I0_prev_used = st.s.I0;
   st.I1_prev_used = st.s.I1;
   st.s.V = V; st.s.I0 = I0n; st.s.I1 = I1n; st.s.com = com; st.s.com_rate = com_rate;
   st.last_update = j;
+}
+SALP_HD void make_coefs(const SalpDerived& dv, const float dir[3], const ShapeFront& f, Coef32& g) {
+  make_coefs(dv, dir, f.jet_on != 0.0f, 0.5f * (dv.init_length_f - f.dl), 0.5f * (dv.init_width_f + f.dl),
+             f.I_rate0, f.I_rate1, f.dV_dt, f.com, f.com_rate, f.com_acc, g);
+}
+SALP_HD void shape_update_at(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c, double t,
+                             const float dir[3], int j, int k_T0, int k_jet, ShapeTrack& st, Coef32& g) {
+  ShapeFront f;
+  shape_front(p, dv, c, t, j, k_T0, k_jet, st, f);
+  make_coefs(dv, dir, f, g);
 }
 
 // ---- building blocks shared by the fused loop below and the pipeline kernel ------------------

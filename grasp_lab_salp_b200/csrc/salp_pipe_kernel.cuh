@@ -1,39 +1,45 @@
-// salp_pipe_kernel.cuh -- the small-batch step kernel: shape producer warp + motion consumer warp.
+// salp_pipe_kernel.cuh -- the small-batch step kernel: two shape-producer warps + one motion warp.
 //
 // With a few thousand envs the GPU is almost empty (4096 envs = 128 warps on 592 SM sub-partitions)
 // and the step time is K_max (~1340 substeps of the slowest env) x the time ONE warp needs per
-// substep -- and that warp is bound by instruction issue: 365 instructions per substep while the
-// body shape moves (kinematics + dynamics + the fp64 shape chain and its ~100-instruction
+// substep -- and that warp is bound by instruction issue: ~340 instructions per substep while the
+// body shape moves (kinematics + dynamics + the fp64 shape chain and its ~90-instruction
 // coefficient set), 166 afterwards.  But the shape and every coefficient derived from it depend on
-// the action and the substep index only, never on the motion state.  So one block of TWO warps
-// owns 32 envs:
-//   * warp 1 (producer) runs the shape updates j = 1..W ahead of time and publishes each
-//     coefficient set in a shared-memory ring (slot j % 32, 28 floats per lane, 128-bit accesses);
-//   * warp 0 (consumer) runs the same software-pipelined kin(k-1) || dyn(k) loop as the fused
-//     kernel, loading its coefficients from the ring instead of computing them.
-// Each warp sits on its own SM sub-partition.  Hand-off is chunk-granular (8 substeps, 4 chunks in
-// flight) on named barriers: bar.arrive on the side that is done with a chunk, bar.sync on the
-// side that needs it, so neither warp waits unless the other has fallen a whole chunk behind.
-// The two warps execute exactly the arithmetic of run_cycle_mixed (same functions, same fixed
-// 32-substep grouping of the fp32 chunk sums): results are bit-identical with the fused kernel
-// (tests/test_gpu_parity.py::test_pipeline_kernel_matches_fused_kernel).
+// the action and the substep index only, never on the motion state.  So one block of THREE warps
+// owns 32 envs, each warp on its own SM sub-partition:
+//   * warp 2 (front)    : shape_front(j), j = 1..W -- the fp64 shape chain and its backward
+//                         differences, 8 floats per lane and substep into ring 1;
+//   * warp 1 (coefs)    : make_coefs(j) from ring 1 -- the stateless fp32 coefficient set, 28 floats
+//                         per lane and substep into ring 2;
+//   * warp 0 (consumer) : the same software-pipelined kin(k-1) || dyn(k) loop as the fused kernel,
+//                         loading its coefficients from ring 2 instead of computing them.
+// Hand-off is chunk-granular (8 substeps; 3 resp. 4 chunks in flight) on named barriers:
+// bar.arrive on the side that is done with a chunk, bar.sync on the side that needs it, so no warp
+// waits unless its neighbour has fallen a whole chunk behind.  The three warps execute the
+// functions of run_cycle_mixed (same fixed 32-substep grouping of the fp32 chunk sums); results
+// agree with the fused kernel to fp32 rounding (the compiler contracts a*b+c differently in the
+// two kernels; tests/test_gpu_parity.py::test_pipeline_kernel_matches_fused_kernel).
 #pragma once
 #include "salp_env.cuh"
 
 #define SALP_PIPE_CHUNK 8
-#define SALP_PIPE_NBUF 4
-#define SALP_PIPE_SLOTS (SALP_PIPE_CHUNK * SALP_PIPE_NBUF)
+#define SALP_PIPE_NBUF1 3
+#define SALP_PIPE_NBUF2 4
+#define SALP_PIPE_SLOTS1 (SALP_PIPE_CHUNK * SALP_PIPE_NBUF1)
+#define SALP_PIPE_SLOTS2 (SALP_PIPE_CHUNK * SALP_PIPE_NBUF2)
 #define SALP_PIPE_NCOEF 28
-#define SALP_PIPE_THREADS 64
+#define SALP_PIPE_THREADS 96
 
 struct PipeShared {
-  float ring[SALP_PIPE_SLOTS][32][SALP_PIPE_NCOEF];     // Coef32 of substep j in slot j % SLOTS, one 112-byte row per lane
-  double merge[9][32];                                  // the producer's final shape state, for the consumer's epilogue
+  float ring2[SALP_PIPE_SLOTS2][32][SALP_PIPE_NCOEF];   // Coef32 of substep j in slot j % SLOTS2, one 112-byte row per lane
+  float ring1[SALP_PIPE_SLOTS1][32][8];                 // ShapeFront of substep j in slot j % SLOTS1
+  double merge[9][32];                                  // the front warp's final shape state, for the consumer's epilogue
 };
 static inline size_t pipe_smem_bytes(const SalpParams& p) {
   return sizeof(PipeShared) + sizeof(float) * 2 * 32 * (SALP_OBS_BASE + 2 * p.num_obstacles);
 }
 
+// named barriers (0 is __syncthreads); every hand-off involves two warps = 64 threads
 __device__ __forceinline__ void pipe_bar_sync(int id) {
   asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
 }
@@ -41,10 +47,22 @@ __device__ __forceinline__ void pipe_bar_arrive(int id) {
   __threadfence_block();
   asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory");
 }
-// named barriers (0 is __syncthreads)
-#define PIPE_FULL(b) (1 + (b))
-#define PIPE_EMPTY(b) (1 + SALP_PIPE_NBUF + (b))
+#define PIPE_FULL1(b) (1 + (b))
+#define PIPE_EMPTY1(b) (1 + SALP_PIPE_NBUF1 + (b))
+#define PIPE_FULL2(b) (1 + 2 * SALP_PIPE_NBUF1 + (b))
+#define PIPE_EMPTY2(b) (1 + 2 * SALP_PIPE_NBUF1 + SALP_PIPE_NBUF2 + (b))
 
+__device__ __forceinline__ void front_store(const ShapeFront& f, float* row) {
+  float4* q = reinterpret_cast<float4*>(row);
+  q[0] = make_float4(f.dl, f.I_rate0, f.I_rate1, f.dV_dt);
+  q[1] = make_float4(f.com, f.com_rate, f.com_acc, f.jet_on);
+}
+__device__ __forceinline__ void front_load(ShapeFront& f, const float* row) {
+  const float4* q = reinterpret_cast<const float4*>(row);
+  float4 a = q[0], b = q[1];
+  f.dl = a.x; f.I_rate0 = a.y; f.I_rate1 = a.z; f.dV_dt = a.w;
+  f.com = b.x; f.com_rate = b.y; f.com_acc = b.z; f.jet_on = b.w;
+}
 __device__ __forceinline__ void coef_store(const Coef32& g, float* row) {
   float4* q = reinterpret_cast<float4*>(row);
   q[0] = make_float4(g.aj[0], g.aj[1], g.aj[2], g.kdm[0]);
@@ -78,7 +96,7 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
   const bool live = i < v.n;
   constexpr int C = SALP_PIPE_CHUNK;
 
-  // Both warps read the env's action and state themselves (reads only; every write happens in the
+  // All three warps read the env's action and state themselves (reads only; every write happens in the
   // consumer's epilogue after the block-wide barrier) and derive the same integer plan.
   StepCtx cx;
   Body64 b;
@@ -103,44 +121,46 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
   const int nch = (Wmax + C - 1) / C;
   const float dir[3] = {(float)cx.plan.dir[0], (float)cx.plan.dir[1], (float)cx.plan.dir[2]};
 
-  if (warp == 1) {
-    // ---------------- producer: coefficient sets g_j, j = 1..kA ----------------
+  if (warp == 2) {
+    // ---------------- front: fp64 shape chain + backward differences, j = 1..kA ----------------
     ShapeTrack st;
-    Coef32 g;
-    if (K > 0) mixed_init_shape(p, dv, b, dir, st, g);
+    if (K > 0) {
+      Coef32 g0;
+      mixed_init_shape(p, dv, b, dir, st, g0);
+    }
     double tj = v.time_table[1];                   // carried by the same additions as the table (robot.py:674)
     int j = 1;
     for (int c = 0; c < nch; c++) {
-      if (c >= SALP_PIPE_NBUF) pipe_bar_sync(PIPE_EMPTY(c % SALP_PIPE_NBUF));
+      if (c >= SALP_PIPE_NBUF1) pipe_bar_sync(PIPE_EMPTY1(c % SALP_PIPE_NBUF1));
       const int je = (c + 1) * C < Wmax ? (c + 1) * C : Wmax;
       // two updates per trip: consecutive updates are independent chains until their backward
-      // differences (shape64_step carries nothing), so the scheduler overlaps them and the warp is
-      // bound by instruction issue instead of by the latency of one fp64 chain
+      // differences (shape64_step carries nothing), so the scheduler overlaps them
       while (j <= je) {
         const double tj1 = rn::dadd(tj, p.dt);
+        ShapeFront f0, f1;
         if (j + 1 <= je) {
           if (j + 1 <= kA) {
-            shape_update_at(p, dv, cx.plan, tj, dir, j, pp.k_T0, pp.k_jet, st, g);
-            coef_store(g, &sh.ring[j % SALP_PIPE_SLOTS][lane][0]);
-            shape_update_at(p, dv, cx.plan, tj1, dir, j + 1, pp.k_T0, pp.k_jet, st, g);
-            coef_store(g, &sh.ring[(j + 1) % SALP_PIPE_SLOTS][lane][0]);
+            shape_front(p, dv, cx.plan, tj, j, pp.k_T0, pp.k_jet, st, f0);
+            shape_front(p, dv, cx.plan, tj1, j + 1, pp.k_T0, pp.k_jet, st, f1);
+            front_store(f0, &sh.ring1[j % SALP_PIPE_SLOTS1][lane][0]);
+            front_store(f1, &sh.ring1[(j + 1) % SALP_PIPE_SLOTS1][lane][0]);
           } else if (j <= kA) {
-            shape_update_at(p, dv, cx.plan, tj, dir, j, pp.k_T0, pp.k_jet, st, g);
-            coef_store(g, &sh.ring[j % SALP_PIPE_SLOTS][lane][0]);
+            shape_front(p, dv, cx.plan, tj, j, pp.k_T0, pp.k_jet, st, f0);
+            front_store(f0, &sh.ring1[j % SALP_PIPE_SLOTS1][lane][0]);
           }
           tj = rn::dadd(tj1, p.dt);
           j += 2;
         } else {
           if (j <= kA) {
-            shape_update_at(p, dv, cx.plan, tj, dir, j, pp.k_T0, pp.k_jet, st, g);
-            coef_store(g, &sh.ring[j % SALP_PIPE_SLOTS][lane][0]);
+            shape_front(p, dv, cx.plan, tj, j, pp.k_T0, pp.k_jet, st, f0);
+            front_store(f0, &sh.ring1[j % SALP_PIPE_SLOTS1][lane][0]);
           }
           tj = tj1;
           j += 1;
         }
       }
       __syncwarp();
-      pipe_bar_arrive(PIPE_FULL(c % SALP_PIPE_NBUF));
+      pipe_bar_arrive(PIPE_FULL1(c % SALP_PIPE_NBUF1));
     }
     if (K > 0) {
       mixed_finish_shape(p, st, K, b);
@@ -148,6 +168,43 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
       sh.merge[3][lane] = b.prevI[0]; sh.merge[4][lane] = b.prevI[1];
       sh.merge[5][lane] = b.com; sh.merge[6][lane] = b.com_rate; sh.merge[7][lane] = b.prev_com_rate;
       sh.merge[8][lane] = b.com_acc;
+    }
+  } else if (warp == 1) {
+    // ---------------- coefs: the stateless fp32 coefficient set of each ShapeFront ----------------
+    int j = 1;
+    for (int c = 0; c < nch; c++) {
+      pipe_bar_sync(PIPE_FULL1(c % SALP_PIPE_NBUF1));
+      if (c >= SALP_PIPE_NBUF2) pipe_bar_sync(PIPE_EMPTY2(c % SALP_PIPE_NBUF2));
+      const int je = (c + 1) * C < Wmax ? (c + 1) * C : Wmax;
+      while (j <= je) {
+        ShapeFront f0, f1;
+        Coef32 g0, g1;
+        if (j + 1 <= je) {
+          if (j + 1 <= kA) {
+            front_load(f0, &sh.ring1[j % SALP_PIPE_SLOTS1][lane][0]);
+            front_load(f1, &sh.ring1[(j + 1) % SALP_PIPE_SLOTS1][lane][0]);
+            make_coefs(dv, dir, f0, g0);
+            make_coefs(dv, dir, f1, g1);
+            coef_store(g0, &sh.ring2[j % SALP_PIPE_SLOTS2][lane][0]);
+            coef_store(g1, &sh.ring2[(j + 1) % SALP_PIPE_SLOTS2][lane][0]);
+          } else if (j <= kA) {
+            front_load(f0, &sh.ring1[j % SALP_PIPE_SLOTS1][lane][0]);
+            make_coefs(dv, dir, f0, g0);
+            coef_store(g0, &sh.ring2[j % SALP_PIPE_SLOTS2][lane][0]);
+          }
+          j += 2;
+        } else {
+          if (j <= kA) {
+            front_load(f0, &sh.ring1[j % SALP_PIPE_SLOTS1][lane][0]);
+            make_coefs(dv, dir, f0, g0);
+            coef_store(g0, &sh.ring2[j % SALP_PIPE_SLOTS2][lane][0]);
+          }
+          j += 1;
+        }
+      }
+      __syncwarp();
+      pipe_bar_arrive(PIPE_EMPTY1(c % SALP_PIPE_NBUF1));
+      pipe_bar_arrive(PIPE_FULL2(c % SALP_PIPE_NBUF2));
     }
   } else {
     // ---------------- consumer: kin(k-1) || dyn(k), coefficients from the ring ----------------
@@ -163,18 +220,18 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
     int kk = 1;
     const int WA = Wmax < Kw - 1 ? Wmax : Kw - 1;   // iterations kk = 1..K-1 exist; those <= W load g_kk
     for (int c = 0; c < nch; c++) {
-      pipe_bar_sync(PIPE_FULL(c % SALP_PIPE_NBUF));
+      pipe_bar_sync(PIPE_FULL2(c % SALP_PIPE_NBUF2));
       const int ce = (c + 1) * C < WA ? (c + 1) * C : WA;
       for (; kk <= ce; kk++) {
         if (kk < K) {
-          coef_load(g, &sh.ring[kk % SALP_PIPE_SLOTS][lane][0]);
+          coef_load(g, &sh.ring2[kk % SALP_PIPE_SLOTS2][lane][0]);
           kin_step(dv, s);
           dyn_step(dv, g, s);
           if ((kk & (SALP_MIXED_CHUNK - 1)) == 0) flush_chunk(b, s);
         }
       }
       __syncwarp();
-      pipe_bar_arrive(PIPE_EMPTY(c % SALP_PIPE_NBUF));
+      pipe_bar_arrive(PIPE_EMPTY2(c % SALP_PIPE_NBUF2));
     }
     // the coast: the fused kernel's lean loop, same fixed chunk boundaries
     int k = kk;
