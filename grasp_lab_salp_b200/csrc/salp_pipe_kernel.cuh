@@ -53,8 +53,9 @@ static inline size_t pipe_smem_bytes(const SalpParams& p) {
 __device__ __forceinline__ void pipe_bar_sync(int id) {
   asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
 }
+// (no fence: a completed barrier orders the shared-memory accesses its participants made before
+//  arriving -- the producer/consumer idiom of the PTX ISA's bar.arrive / bar.sync example)
 __device__ __forceinline__ void pipe_bar_arrive(int id) {
-  __threadfence_block();
   asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory");
 }
 #define PIPE_FULL1(b) (1 + (b))
