@@ -31,11 +31,11 @@
 
 #define SALP_PIPE_CHUNK 8
 #define SALP_PIPE_NBUF1 2
-#define SALP_PIPE_NBUF2 3
-#define SALP_PIPE_NBUF3 2
+#define SALP_PIPE_NBUF2 2
+#define SALP_PIPE_NBUF3 3
 #define SALP_PIPE_SLOTS1 (SALP_PIPE_CHUNK * SALP_PIPE_NBUF1)
 #define SALP_PIPE_SLOTS2 (SALP_PIPE_CHUNK * SALP_PIPE_NBUF2)
-#define SALP_PIPE_SLOTS3 32      // substep k in slot k % 32: at most 2 chunks (+ substep 0) = 17 entries in flight
+#define SALP_PIPE_SLOTS3 32      // substep k in slot k % 32: at most 3 chunks (+ substep 0) = 25 entries in flight
 #define SALP_PIPE_NCOEF 28
 #define SALP_PIPE_THREADS 128
 
@@ -276,12 +276,30 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
     for (int c = 0; c < nchK; c++) {
       pipe_bar_sync(PIPE_FULL3(c % SALP_PIPE_NBUF3));
       const int ce = (c + 1) * C < Kw - 1 ? (c + 1) * C : Kw - 1;
-      for (; kk <= ce; kk++) {
-        if (kk < K) {
-          vw_load(s, &sh.ring3[kk % SALP_PIPE_SLOTS3][lane][0]);
-          kin_step(dv, s);
-          // the fused loop flushes after iteration 32 m (kinematic updates 0..32 m - 1 done) if 32 m < K
-          if (((kk + 1) & (SALP_MIXED_CHUNK - 1)) == 0 && kk + 1 < K) flush_chunk(b, s);
+      // two substeps per trip where possible: the rotation of v into the world frame and the
+      // integrals of substep k overlap the Euler-rate chain of substep k + 1
+      // (kk and the trip structure stay warp-uniform; only the work inside is per lane)
+      while (kk <= ce) {
+        if (kk + 1 <= ce && ((kk + 1) & (SALP_MIXED_CHUNK - 1)) != 0) {       // no flush between the two
+          if (kk + 1 < K) {
+            vw_load(s, &sh.ring3[kk % SALP_PIPE_SLOTS3][lane][0]);
+            kin_step(dv, s);
+            vw_load(s, &sh.ring3[(kk + 1) % SALP_PIPE_SLOTS3][lane][0]);
+            kin_step(dv, s);
+            // the fused loop flushes after iteration 32 m (kinematic updates 0..32 m - 1 done) if 32 m < K
+            if (((kk + 2) & (SALP_MIXED_CHUNK - 1)) == 0 && kk + 2 < K) flush_chunk(b, s);
+          } else if (kk < K) {
+            vw_load(s, &sh.ring3[kk % SALP_PIPE_SLOTS3][lane][0]);
+            kin_step(dv, s);
+          }
+          kk += 2;
+        } else {
+          if (kk < K) {
+            vw_load(s, &sh.ring3[kk % SALP_PIPE_SLOTS3][lane][0]);
+            kin_step(dv, s);
+            if (((kk + 1) & (SALP_MIXED_CHUNK - 1)) == 0 && kk + 1 < K) flush_chunk(b, s);
+          }
+          kk += 1;
         }
       }
       __syncwarp();
