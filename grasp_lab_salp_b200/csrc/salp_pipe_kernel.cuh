@@ -1,49 +1,41 @@
-// salp_pipe_kernel.cuh -- the small-batch step kernel: a four-warp feed-forward pipeline.
+// salp_pipe_kernel.cuh -- the small-batch step kernel: two shape-producer warps + one motion warp.
 //
 // With a few thousand envs the GPU is almost empty (4096 envs = 128 warps on 592 SM sub-partitions)
 // and the step time is K_max (~1340 substeps of the slowest env) x the time ONE warp needs per
 // substep -- and that warp is bound by instruction issue: ~340 instructions per substep while the
 // body shape moves (kinematics + dynamics + the fp64 shape chain and its ~90-instruction
-// coefficient set), 166 afterwards.  But the substep is feed-forward:
-//
-//     front(j) -> coefs(j) -> dyn(j) -> kin(j)
-//
-//   * the shape and every coefficient derived from it depend on the action and on j only;
-//   * the Newton/Euler equations + velocity update (dyn) need the coefficients and (v, w);
-//   * the Euler angles / world position / body-frame integrals (kin) only consume (v, w) and never
-//     feed back (there is no gravity or current in the reference's model).
-// So one block of FOUR warps owns 32 envs, each warp on its own SM sub-partition:
-//   * warp 2 (front) : shape_front(j), j = 1..W -- the fp64 shape chain and its backward
-//                      differences, 8 floats per lane and substep into ring 1;
-//   * warp 1 (coefs) : make_coefs(j) from ring 1 -- the stateless fp32 coefficient set, 28 floats
-//                      per lane and substep into ring 2;
-//   * warp 0 (dyn)   : the dyn recurrence, the only true critical path (~95 instructions per
-//                      substep); coefficients from ring 2 while the shape moves, (v, w) into ring 3;
-//   * warp 3 (kin)   : integrates the kinematics behind it from ring 3.
-// Hand-off is chunk-granular (8 substeps, 2-3 chunks in flight per ring) on named barriers:
+// coefficient set), 166 afterwards.  But the shape and every coefficient derived from it depend on
+// the action and the substep index only, never on the motion state.  So one block of THREE warps
+// owns 32 envs, each warp on its own SM sub-partition:
+//   * warp 2 (front)    : shape_front(j), j = 1..W -- the fp64 shape chain and its backward
+//                         differences, 8 floats per lane and substep into ring 1;
+//   * warp 1 (coefs)    : make_coefs(j) from ring 1 -- the stateless fp32 coefficient set, 28 floats
+//                         per lane and substep into ring 2;
+//   * warp 0 (consumer) : the same software-pipelined kin(k-1) || dyn(k) loop as the fused kernel,
+//                         loading its coefficients from ring 2 instead of computing them.
+// Hand-off is chunk-granular (8 substeps; 3 resp. 4 chunks in flight) on named barriers:
 // bar.arrive on the side that is done with a chunk, bar.sync on the side that needs it, so no warp
-// waits unless its neighbour has fallen a whole chunk behind.  The warps execute the functions of
-// run_cycle_mixed (same fixed 32-substep grouping of the fp32 chunk sums); results agree with the
-// fused kernel to fp32 rounding (the compiler contracts a*b+c differently in the two kernels;
-// tests/test_gpu_parity.py::test_pipeline_kernel_matches_fused_kernel).
+// waits unless its neighbour has fallen a whole chunk behind.  The three warps execute the
+// functions of run_cycle_mixed (same fixed 32-substep grouping of the fp32 chunk sums); results
+// agree with the fused kernel to fp32 rounding (the compiler contracts a*b+c differently in the
+// two kernels; tests/test_gpu_parity.py::test_pipeline_kernel_matches_fused_kernel).
+// (Splitting the consumer further into a dyn warp and a kin warp was measured slower, 0.203 vs
+// 0.190 ms per 4096-env step: in one warp the two chains fill each other's latency shadows.)
 #pragma once
 #include "salp_env.cuh"
 
 #define SALP_PIPE_CHUNK 8
-#define SALP_PIPE_NBUF1 2
-#define SALP_PIPE_NBUF2 2
-#define SALP_PIPE_NBUF3 3
+#define SALP_PIPE_NBUF1 3
+#define SALP_PIPE_NBUF2 4
 #define SALP_PIPE_SLOTS1 (SALP_PIPE_CHUNK * SALP_PIPE_NBUF1)
 #define SALP_PIPE_SLOTS2 (SALP_PIPE_CHUNK * SALP_PIPE_NBUF2)
-#define SALP_PIPE_SLOTS3 32      // substep k in slot k % 32: at most 3 chunks (+ substep 0) = 25 entries in flight
 #define SALP_PIPE_NCOEF 28
-#define SALP_PIPE_THREADS 128
+#define SALP_PIPE_THREADS 96
 
 struct PipeShared {
   float ring2[SALP_PIPE_SLOTS2][32][SALP_PIPE_NCOEF];   // Coef32 of substep j in slot j % SLOTS2, one 112-byte row per lane
   float ring1[SALP_PIPE_SLOTS1][32][8];                 // ShapeFront of substep j in slot j % SLOTS1
-  float ring3[SALP_PIPE_SLOTS3][32][8];                 // (v, w) after dyn(k) in slot k % SLOTS3
-  double merge[22][32];                                 // final shape (front) and kinematic (kin) state, for warp 0's epilogue
+  double merge[9][32];                                  // the front warp's final shape state, for the consumer's epilogue
 };
 static inline size_t pipe_smem_bytes(const SalpParams& p) {
   return sizeof(PipeShared) + sizeof(float) * 2 * 32 * (SALP_OBS_BASE + 2 * p.num_obstacles);
@@ -62,8 +54,6 @@ __device__ __forceinline__ void pipe_bar_arrive(int id) {
 #define PIPE_EMPTY1(b) (1 + SALP_PIPE_NBUF1 + (b))
 #define PIPE_FULL2(b) (1 + 2 * SALP_PIPE_NBUF1 + (b))
 #define PIPE_EMPTY2(b) (1 + 2 * SALP_PIPE_NBUF1 + SALP_PIPE_NBUF2 + (b))
-#define PIPE_FULL3(b) (1 + 2 * SALP_PIPE_NBUF1 + 2 * SALP_PIPE_NBUF2 + (b))
-#define PIPE_EMPTY3(b) (1 + 2 * SALP_PIPE_NBUF1 + 2 * SALP_PIPE_NBUF2 + SALP_PIPE_NBUF3 + (b))
 
 __device__ __forceinline__ void front_store(const ShapeFront& f, float* row) {
   float4* q = reinterpret_cast<float4*>(row);
@@ -75,17 +65,6 @@ __device__ __forceinline__ void front_load(ShapeFront& f, const float* row) {
   float4 a = q[0], b = q[1];
   f.dl = a.x; f.I_rate0 = a.y; f.I_rate1 = a.z; f.dV_dt = a.w;
   f.com = b.x; f.com_rate = b.y; f.com_acc = b.z; f.jet_on = b.w;
-}
-__device__ __forceinline__ void vw_store(const Motion32& s, float* row) {
-  float4* q = reinterpret_cast<float4*>(row);
-  q[0] = make_float4(s.v0, s.v1, s.v2, s.w0);
-  q[1] = make_float4(s.w1, s.w2, 0.f, 0.f);
-}
-__device__ __forceinline__ void vw_load(Motion32& s, const float* row) {
-  const float4* q = reinterpret_cast<const float4*>(row);
-  float4 a = q[0], b = q[1];
-  s.v0 = a.x; s.v1 = a.y; s.v2 = a.z; s.w0 = a.w;
-  s.w1 = b.x; s.w2 = b.y;
 }
 __device__ __forceinline__ void coef_store(const Coef32& g, float* row) {
   float4* q = reinterpret_cast<float4*>(row);
@@ -142,8 +121,7 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
   const int Kw = __reduce_max_sync(0xffffffffu, K);
   const int kA = W < K ? W : K;
   const int Wmax = W < Kw ? W : Kw;
-  const int nch = (Wmax + C - 1) / C;            // chunks of shape updates j = 1..Wmax
-  const int nchK = Kw > 0 ? (Kw - 1 + C - 1) / C + (Kw == 1 ? 1 : 0) : 0;   // chunks of substeps 1..Kw-1 (one chunk if only substep 0 exists)
+  const int nch = (Wmax + C - 1) / C;
   const float dir[3] = {(float)cx.plan.dir[0], (float)cx.plan.dir[1], (float)cx.plan.dir[2]};
 
   if (warp == 2) {
@@ -231,88 +209,49 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
       pipe_bar_arrive(PIPE_EMPTY1(c % SALP_PIPE_NBUF1));
       pipe_bar_arrive(PIPE_FULL2(c % SALP_PIPE_NBUF2));
     }
-  } else if (warp == 0) {
-    // ---------------- dyn: the recurrence; substeps k = 0..K-1, chunk c = substeps 8c+1..8c+8 (+ substep 0 in chunk 0) ----------------
+  } else {
+    // ---------------- consumer: kin(k-1) || dyn(k), coefficients from the ring ----------------
     Motion32 s;
     Coef32 g;
     if (K > 0) {
       ShapeTrack st0;
       mixed_init_shape(p, dv, b, dir, st0, g);      // g_0 (once; cheaper than a hand-off)
       mixed_init_dyn(b, s);
+      mixed_init_kin(b, s);
       dyn_step(dv, g, s);
-      vw_store(s, &sh.ring3[0][lane][0]);
     }
     int kk = 1;
-    for (int c = 0; c < nchK; c++) {
-      if (c < nch) pipe_bar_sync(PIPE_FULL2(c % SALP_PIPE_NBUF2));
-      if (c >= SALP_PIPE_NBUF3) pipe_bar_sync(PIPE_EMPTY3(c % SALP_PIPE_NBUF3));
-      const int ce = (c + 1) * C < Kw - 1 ? (c + 1) * C : Kw - 1;
-      if (c < nch) {
-        for (; kk <= ce; kk++) {
-          if (kk < K) {
-            if (kk <= W) coef_load(g, &sh.ring2[kk % SALP_PIPE_SLOTS2][lane][0]);
-            dyn_step(dv, g, s);
-            vw_store(s, &sh.ring3[kk % SALP_PIPE_SLOTS3][lane][0]);
-          }
-        }
-      } else {
-        for (; kk <= ce; kk++) {
-          if (kk < K) {
-            dyn_step(dv, g, s);
-            vw_store(s, &sh.ring3[kk % SALP_PIPE_SLOTS3][lane][0]);
-          }
+    const int WA = Wmax < Kw - 1 ? Wmax : Kw - 1;   // iterations kk = 1..K-1 exist; those <= W load g_kk
+    for (int c = 0; c < nch; c++) {
+      pipe_bar_sync(PIPE_FULL2(c % SALP_PIPE_NBUF2));
+      const int ce = (c + 1) * C < WA ? (c + 1) * C : WA;
+      for (; kk <= ce; kk++) {
+        if (kk < K) {
+          coef_load(g, &sh.ring2[kk % SALP_PIPE_SLOTS2][lane][0]);
+          kin_step(dv, s);
+          dyn_step(dv, g, s);
+          if ((kk & (SALP_MIXED_CHUNK - 1)) == 0) flush_chunk(b, s);
         }
       }
       __syncwarp();
-      if (c < nch) pipe_bar_arrive(PIPE_EMPTY2(c % SALP_PIPE_NBUF2));
-      pipe_bar_arrive(PIPE_FULL3(c % SALP_PIPE_NBUF3));
+      pipe_bar_arrive(PIPE_EMPTY2(c % SALP_PIPE_NBUF2));
     }
-    if (K > 0) mixed_finish_dyn(s, b);
-  } else {
-    // ---------------- kin: Euler angles, world position, body-frame integrals; kin(k) from (v, w) after dyn(k) ----------------
-    Motion32 s;
-    if (K > 0) mixed_init_kin(b, s);
-    int kk = 0;
-    for (int c = 0; c < nchK; c++) {
-      pipe_bar_sync(PIPE_FULL3(c % SALP_PIPE_NBUF3));
-      const int ce = (c + 1) * C < Kw - 1 ? (c + 1) * C : Kw - 1;
-      // two substeps per trip where possible: the rotation of v into the world frame and the
-      // integrals of substep k overlap the Euler-rate chain of substep k + 1
-      // (kk and the trip structure stay warp-uniform; only the work inside is per lane)
-      while (kk <= ce) {
-        if (kk + 1 <= ce && ((kk + 1) & (SALP_MIXED_CHUNK - 1)) != 0) {       // no flush between the two
-          if (kk + 1 < K) {
-            vw_load(s, &sh.ring3[kk % SALP_PIPE_SLOTS3][lane][0]);
-            kin_step(dv, s);
-            vw_load(s, &sh.ring3[(kk + 1) % SALP_PIPE_SLOTS3][lane][0]);
-            kin_step(dv, s);
-            // the fused loop flushes after iteration 32 m (kinematic updates 0..32 m - 1 done) if 32 m < K
-            if (((kk + 2) & (SALP_MIXED_CHUNK - 1)) == 0 && kk + 2 < K) flush_chunk(b, s);
-          } else if (kk < K) {
-            vw_load(s, &sh.ring3[kk % SALP_PIPE_SLOTS3][lane][0]);
-            kin_step(dv, s);
-          }
-          kk += 2;
-        } else {
-          if (kk < K) {
-            vw_load(s, &sh.ring3[kk % SALP_PIPE_SLOTS3][lane][0]);
-            kin_step(dv, s);
-            if (((kk + 1) & (SALP_MIXED_CHUNK - 1)) == 0 && kk + 1 < K) flush_chunk(b, s);
-          }
-          kk += 1;
-        }
+    // the coast: the fused kernel's lean loop, same fixed chunk boundaries
+    int k = kk;
+    while (k < K) {
+      const int boundary = ((k - 1) & ~(SALP_MIXED_CHUNK - 1)) + SALP_MIXED_CHUNK + 1;
+      const int cend = boundary < K ? boundary : K;
+      for (; k < cend; k++) {
+        kin_step(dv, s);
+        dyn_step(dv, g, s);
       }
-      __syncwarp();
-      pipe_bar_arrive(PIPE_EMPTY3(c % SALP_PIPE_NBUF3));
+      if (k == boundary) flush_chunk(b, s);
     }
     if (K > 0) {
+      kin_step(dv, s);
       flush_chunk(b, s);
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        sh.merge[9 + k][lane] = b.pw[k]; sh.merge[12 + k][lane] = b.pos[k];
-        sh.merge[15 + k][lane] = b.ang[k]; sh.merge[18 + k][lane] = b.eul[k];
-      }
-      sh.merge[21][lane] = (double)sqrtf(s.vw0 * s.vw0 + s.vw1 * s.vw1);
+      mixed_finish_dyn(s, b);
+      b.speed_world = (double)sqrtf(s.vw0 * s.vw0 + s.vw1 * s.vw1);
     }
   }
   __syncthreads();
@@ -324,12 +263,6 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
       b.prevI[0] = sh.merge[3][lane]; b.prevI[1] = sh.merge[4][lane]; b.prevI[2] = sh.merge[4][lane];
       b.com = sh.merge[5][lane]; b.prev_com = sh.merge[5][lane]; b.com_rate = sh.merge[6][lane];
       b.prev_com_rate = sh.merge[7][lane]; b.com_acc = sh.merge[8][lane];
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        b.pw[k] = sh.merge[9 + k][lane]; b.pos[k] = sh.merge[12 + k][lane];
-        b.ang[k] = sh.merge[15 + k][lane]; b.eul[k] = sh.merge[18 + k][lane];
-      }
-      b.speed_world = sh.merge[21][lane];
       t = v.time_table[K];
       b.phase = phase_at(cx.plan, t);
     }
