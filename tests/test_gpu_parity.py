@@ -208,10 +208,12 @@ def test_full_size_mixed_vs_f64_trajectory_equivalence():
     f64.check()
 
 
-def test_shard_invariance():
+@pytest.mark.parametrize("n", [512, 12288])      # pipeline kernel (<= 4736 envs per handle) / fused kernel
+def test_shard_invariance(n):
     """Multi-GPU sharding rule: envs [0,N) on one handle == two handles of N/2 with
-    env_id_offset, bit for bit (per-env Philox streams are keyed by the GLOBAL env id)."""
-    n, T = 512, 20
+    env_id_offset, bit for bit (per-env Philox streams are keyed by the GLOBAL env id; results
+    do not depend on which envs share a warp)."""
+    T = 20 if n <= 4736 else 8
     g = load_golden("ref_random.npz")
     acts = uniform_actions(np.random.default_rng(6), T, n)
     whole = SalpBatch(n, golden_params(g), seed=21)
