@@ -37,8 +37,10 @@ SALP_HD float fast_rcp(float x) {
   return 1.0f / x;
 #endif
 }
-SALP_HD float fast_norm3(float a, float b, float c) {
-  float s = fmaf(a, a, fmaf(b, b, c * c));
+// bc2 = b^2 + c^2, the partial sum on the way (the fictitious force needs w1^2 + w2^2)
+SALP_HD float fast_norm3(float a, float b, float c, float& bc2) {
+  bc2 = fmaf(b, b, c * c);
+  float s = fmaf(a, a, bc2);
 #ifdef __CUDA_ARCH__
   float r;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(s, 1e-35f)));
@@ -48,6 +50,11 @@ SALP_HD float fast_norm3(float a, float b, float c) {
 #else
   return sqrtf(s);
 #endif
+}
+
+SALP_HD float fast_norm3(float a, float b, float c) {
+  float bc2;
+  return fast_norm3(a, b, c, bc2);
 }
 
 // np_sincosf without the separately-rounded steps: same Cody-Waite + minimax kernels (1 ulp),
@@ -158,7 +165,7 @@ struct Coef32 {
   float aj[3];        // F_jet / m                                       (robot.py:937-951)
   float kdm[3];       // -rho/2 area_i Ct_i / m                          (dynamics.py:111-116)
   float mrm[3];       // mass_rate Car_i / m                             (dynamics.py:139)
-  float com, com_rate, com_acc;                                       // robot.py:898-922
+  float com, com_rate2, com_acc;      // centre of mass, 2 x its rate, its acceleration     robot.py:898-922
   float tj1, tj2;     // (arm x F_jet)_i / I_i                           (robot.py:931-935)
   float kqI[3];       // -rho/2 Cr_i area_i dims_i / I_i                 (dynamics.py:120-128)
   float klI[3];       // (ratio -rho/2 Cr_i area_i width - I_rate_i) / I_i   (+ deform torque, :172-174)
@@ -267,7 +274,7 @@ SALP_HD void make_coefs(const SalpDerived& k, const float dir[3], bool jet_on, f
   g.tj1 = -afI * dir[2];
   g.tj2 = afI * dir[1];
   g.com = com;
-  g.com_rate = com_rate;
+  g.com_rate2 = com_rate + com_rate;
   g.com_acc = com_acc;
 }
 
@@ -306,22 +313,34 @@ SALP_HD void ou_step(const SalpDerived& dv, RandCtx& rc, int k) {
   rc.ou_tz = rc.ou_tz * decay + 0.01f * sq * n2;
 }
 
-template <bool NOISE = false>
+// STATIC: the shape has stopped moving (part B of the loop, after the warp-uniform end of every
+// lane's update window + its two settle substeps): com_rate and com_acc are exactly 0 there.
+template <bool NOISE = false, bool STATIC = false>
 SALP_HD void dyn_step(const SalpDerived& dv, const Coef32& g, Motion32& s, RandCtx* rc = nullptr, int k = 0) {
   const float v0 = s.v0, v1 = s.v1, v2 = s.v2, w0 = s.w0, w1 = s.w1, w2 = s.w2;
   float sd = fast_norm3(v0, v1, v2) + dv.ratio_f;               // |v| v + ratio v = v (|v| + ratio)
-  float wn = fast_norm3(w0, w1, w2);
+  float w12;                                                    // w1^2 + w2^2
+  float wn = fast_norm3(w0, w1, w2, w12);
   float ev0 = dv.E[0] * v0, ev1 = dv.E[1] * v1, ev2 = dv.E[2] * v2;
-  float t1 = w2 * g.com, t2 = -w1 * g.com;                      // w x c, c = (com, 0, 0)   robot.py:806-810
-  float fict0 = (w1 * t2 - w2 * t1) + g.com_acc;
-  float fict1 = fmaf(s.al2, g.com, fmaf(2.0f * w2, g.com_rate, -w0 * t2));
-  float fict2 = fmaf(-s.al1, g.com, fmaf(-2.0f * w1, g.com_rate, w0 * t1));
+  const float p12 = w1 * w2, p20 = w2 * w0, p01 = w0 * w1;
+  // fictitious forces of the moving centre of mass c = (com, 0, 0) (robot.py:806-810):
+  //   -(alpha x c) - w x (w x c) - 2 w x c' - c''  with the products of w shared with the Euler equations
+  float fict0, fict1, fict2;
+  if (STATIC) {
+    fict0 = -g.com * w12;
+    fict1 = g.com * (s.al2 + p01);
+    fict2 = g.com * (p20 - s.al1);
+  } else {
+    fict0 = fmaf(-g.com, w12, g.com_acc);
+    fict1 = fmaf(g.com, s.al2 + p01, w2 * g.com_rate2);
+    fict2 = fmaf(g.com, p20 - s.al1, -(w1 * g.com_rate2));
+  }
   float na0 = g.aj[0] + v0 * fmaf(g.kdm[0], sd, -g.mrm[0]) - dv.Ca[0] * s.ac0 - (w1 * ev2 - w2 * ev1) + fict0;
   float na1 = g.aj[1] + v1 * fmaf(g.kdm[1], sd, -g.mrm[1]) - dv.Ca[1] * s.ac1 - (w2 * ev0 - w0 * ev2) + fict1;
   float na2 = g.aj[2] + v2 * fmaf(g.kdm[2], sd, -g.mrm[2]) - dv.Ca[2] * s.ac2 - (w0 * ev1 - w1 * ev0) + fict2;
-  float nl0 = w0 * fmaf(g.kqI[0], wn, g.klI[0]) - dv.Cat[0] * s.al0 - (w1 * w2) * g.JdI[0] - (v1 * v2) * g.AdI[0];
-  float nl1 = g.tj1 + w1 * fmaf(g.kqI[1], wn, g.klI[1]) - dv.Cat[1] * s.al1 - (w2 * w0) * g.JdI[1] - (v2 * v0) * g.AdI[1];
-  float nl2 = g.tj2 + w2 * fmaf(g.kqI[2], wn, g.klI[2]) - dv.Cat[2] * s.al2 - (w0 * w1) * g.JdI[2] - (v0 * v1) * g.AdI[2];
+  float nl0 = w0 * fmaf(g.kqI[0], wn, g.klI[0]) - dv.Cat[0] * s.al0 - p12 * g.JdI[0] - (v1 * v2) * g.AdI[0];
+  float nl1 = g.tj1 + w1 * fmaf(g.kqI[1], wn, g.klI[1]) - dv.Cat[1] * s.al1 - p20 * g.JdI[1] - (v2 * v0) * g.AdI[1];
+  float nl2 = g.tj2 + w2 * fmaf(g.kqI[2], wn, g.klI[2]) - dv.Cat[2] * s.al2 - p01 * g.JdI[2] - (v0 * v1) * g.AdI[2];
   if (NOISE) {        // force_noise / torque_noise join the sums of _newton_equations / _euler_equations
     ou_step(dv, *rc, k);
     na0 = fmaf(rc->ou_fx, g.inv_m, na0);
@@ -341,12 +360,13 @@ SALP_HD void dyn_step(const SalpDerived& dv, const Coef32& g, Motion32& s, RandC
 // (sin, cos)(x) -> (sin, cos)(x + d).  The Taylor kernels are valid for |d| <= 0.55 (a substep moves an
 // Euler angle by ~1e-2 rad); a tumbling body passing the pitch = +-pi/2 singularity of the Euler-rate
 // matrix (long random episodes do, in the reference too) can ask for more for a substep or two:
-// the increment is clamped so that the pair stays a unit vector, and the true angle -- which keeps
-// accumulating the unclamped increment -- re-anchors it at the next flush.
+// the increment is clamped (kin_step) so that the pair stays a unit vector; the fp32 increments
+// and the fp64 angle totals accumulate the same clamped values, so the pair and the angle agree
+// and the pair is re-anchored from the total at the next flush.
 SALP_HD void rotate_small(float d, float& sn, float& cs) {
   // per-substep increments are ~1e-2 rad: sin d = d - d^3/6 + d^5/120, cos d = 1 - d^2/2 + d^4/24
-  // (truncation < 1e-10 there, 2e-7 at the clamp)
-  d = fminf(fmaxf(d, -0.25f), 0.25f);
+  // (truncation < 1e-10 there, 2e-7 at the clamp; dropping the d^5 term was measured to triple the
+  //  error of the violent cycles next to the integrator's stability limit)
   const float d2 = d * d;
   const float sd_ = d * fmaf(d2, fmaf(d2, 8.3333333e-3f, -1.6666667e-1f), 1.0f);
   const float cd_ = fmaf(d2, fmaf(d2, 4.1666667e-2f, -0.5f), 1.0f);
@@ -354,14 +374,18 @@ SALP_HD void rotate_small(float d, float& sn, float& cs) {
   cs = cs * cd_ - sn * sd_;
   sn = ns;
 }
+SALP_HD float clamp_increment(float d) { return fminf(fmaxf(d, -0.25f), 0.25f); }
 SALP_HD void kin_step(const SalpDerived& dv, Motion32& s) {
   const float dt = dv.dt;
   const float v0 = s.v0, v1 = s.v1, v2 = s.v2, w0 = s.w0, w1 = s.w1, w2 = s.w2;
   const float rcth = fast_rcp(s.cth);          // (not Newton-carried: cos(pitch) changes sign when the body tumbles)
   float q = s.sph * w1 + s.cph * w2;
-  float dphi = fmaf(s.sth * rcth, q, w0) * dt;
-  float dtheta = (s.cph * w1 - s.sph * w2) * dt;
-  float dpsi = (q * rcth) * dt;
+  // Euler rates (dynamics.py:21-31): psi' = q / cos(theta), phi' = w0 + sin(theta) psi', theta' = cph w1 - sph w2.
+  // Only the 1 / cos(theta) terms can ask for more than the Taylor kernels take (see above): the
+  // yaw increment is clamped, roll inherits the bound through sin(theta) psi', pitch is clamped too.
+  float dpsi = clamp_increment((q * rcth) * dt);
+  float dphi = fmaf(s.sth, dpsi, w0 * dt);
+  float dtheta = clamp_increment((s.cph * w1 - s.sph * w2) * dt);
   s.phi_lo += dphi;
   s.theta_lo += dtheta;
   s.psi_lo += dpsi;
@@ -595,7 +619,7 @@ SALP_HD int run_cycle_mixed(const SalpParams& p, const SalpDerived& dv, const Cy
     }
     for (; k < cend; k++) {
       kin_step(dv, s);
-      dyn_step<NOISE>(dv, g, s, rc, k);
+      dyn_step<NOISE, true>(dv, g, s, rc, k);       // k >= W: the shape is static
     }
     if (k == boundary) flush_chunk(b, s);       // two-level sums (fp32 chunk partials -> fp64 totals)
   }

@@ -70,7 +70,7 @@ __device__ __forceinline__ void coef_store(const Coef32& g, float* row) {
   float4* q = reinterpret_cast<float4*>(row);
   q[0] = make_float4(g.aj[0], g.aj[1], g.aj[2], g.kdm[0]);
   q[1] = make_float4(g.kdm[1], g.kdm[2], g.mrm[0], g.mrm[1]);
-  q[2] = make_float4(g.mrm[2], g.com, g.com_rate, g.com_acc);
+  q[2] = make_float4(g.mrm[2], g.com, g.com_rate2, g.com_acc);
   q[3] = make_float4(g.tj1, g.tj2, g.kqI[0], g.kqI[1]);
   q[4] = make_float4(g.kqI[2], g.klI[0], g.klI[1], g.klI[2]);
   q[5] = make_float4(g.JdI[0], g.JdI[1], g.JdI[2], g.AdI[0]);
@@ -81,7 +81,7 @@ __device__ __forceinline__ void coef_load(Coef32& g, const float* row) {
   float4 a = q[0], b = q[1], c = q[2], d = q[3], e = q[4], f = q[5], h = q[6];
   g.aj[0] = a.x; g.aj[1] = a.y; g.aj[2] = a.z; g.kdm[0] = a.w;
   g.kdm[1] = b.x; g.kdm[2] = b.y; g.mrm[0] = b.z; g.mrm[1] = b.w;
-  g.mrm[2] = c.x; g.com = c.y; g.com_rate = c.z; g.com_acc = c.w;
+  g.mrm[2] = c.x; g.com = c.y; g.com_rate2 = c.z; g.com_acc = c.w;
   g.tj1 = d.x; g.tj2 = d.y; g.kqI[0] = d.z; g.kqI[1] = d.w;
   g.kqI[2] = e.x; g.klI[0] = e.y; g.klI[1] = e.z; g.klI[2] = e.w;
   g.JdI[0] = f.x; g.JdI[1] = f.y; g.JdI[2] = f.z; g.AdI[0] = f.w;
@@ -243,7 +243,7 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
       const int cend = boundary < K ? boundary : K;
       for (; k < cend; k++) {
         kin_step(dv, s);
-        dyn_step(dv, g, s);
+        dyn_step<false, true>(dv, g, s);            // k > W: the shape is static
       }
       if (k == boundary) flush_chunk(b, s);
     }
