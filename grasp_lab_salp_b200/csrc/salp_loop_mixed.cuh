@@ -325,15 +325,19 @@ SALP_HD void dyn_step(const SalpDerived& dv, const Coef32& g, Motion32& s, RandC
   const float p12 = w1 * w2, p20 = w2 * w0, p01 = w0 * w1;
   // fictitious forces of the moving centre of mass c = (com, 0, 0) (robot.py:806-810):
   //   -(alpha x c) - w x (w x c) - 2 w x c' - c''  with the products of w shared with the Euler equations
+  // (the STATIC form must round exactly like the general one with com_rate2 = com_acc = 0, or results
+  //  would depend on where the warp-uniform loop split falls: explicitly rounded operations, which
+  //  the compiler may not contract with their neighbours)
+  const float t1 = rn::fadd(s.al2, p01), t2 = rn::fsub(p20, s.al1);
   float fict0, fict1, fict2;
   if (STATIC) {
-    fict0 = -g.com * w12;
-    fict1 = g.com * (s.al2 + p01);
-    fict2 = g.com * (p20 - s.al1);
+    fict0 = rn::fmul(-g.com, w12);
+    fict1 = rn::fmul(g.com, t1);
+    fict2 = rn::fmul(g.com, t2);
   } else {
     fict0 = fmaf(-g.com, w12, g.com_acc);
-    fict1 = fmaf(g.com, s.al2 + p01, w2 * g.com_rate2);
-    fict2 = fmaf(g.com, p20 - s.al1, -(w1 * g.com_rate2));
+    fict1 = fmaf(g.com, t1, rn::fmul(w2, g.com_rate2));
+    fict2 = fmaf(g.com, t2, -rn::fmul(w1, g.com_rate2));
   }
   float na0 = g.aj[0] + v0 * fmaf(g.kdm[0], sd, -g.mrm[0]) - dv.Ca[0] * s.ac0 - (w1 * ev2 - w2 * ev1) + fict0;
   float na1 = g.aj[1] + v1 * fmaf(g.kdm[1], sd, -g.mrm[1]) - dv.Ca[1] * s.ac1 - (w2 * ev0 - w0 * ev2) + fict1;
