@@ -290,6 +290,44 @@ def test_pipeline_kernel_matches_fused_kernel():
     fused.check()
 
 
+def test_pipeline_kernel_short_cycles_and_chunk_boundaries():
+    """Cycles of K = 0, 1, 2, ... substeps (contraction 0, coast chosen so that total = K * dt) put
+    the end of the cycle on every position of the pipeline kernel's 8-substep hand-off chunks and
+    of the 32-substep flush boundary; the same coasts again behind a long, a tiny and no
+    contraction with a nozzle turn.  Pipeline kernel (the default at this size) vs the float64
+    oracle at the per-step tolerance, and vs the fused kernel."""
+    ks = np.concatenate([np.arange(0, 42), [63, 64, 65, 66, 95, 96, 97, 127, 128, 129]])
+    m = len(ks)
+    n = 4 * m
+    acts = np.zeros((n, 3), np.float32)
+    # refill(0) = -0.45, jet(0) = -0.125: total = 0 + jet + coast  ->  coast = 0.125 + (K - 0.5) * dt
+    coast = 0.125 + (np.tile(ks, 4) - 0.5) * 0.01
+    acts[:, 1] = np.where(np.tile(ks, 4) > 0, coast / 10.0, 0.0)
+    acts[m:2 * m, 0] = 0.3            # a real contraction (long shape motion) in front of the same coasts
+    acts[2 * m:3 * m, 0] = 0.05       # a tiny one
+    acts[3 * m:, 2] = 0.7             # nozzle turn only
+    prod, orc = _pair(n, PRECISION_MIXED)
+    probe = OracleVecEnv(n, prod.params, seed=3)
+    probe.reset()
+    probe.step(acts)
+    np.testing.assert_array_equal(probe.substeps[:m], ks)          # the crafted coasts give K = 0, 1, 2, ...
+    report = {}
+    lockstep_compare(prod, orc, np.repeat(acts[None], 3, axis=0), resync=True, rtol=TOL_MIXED["rtol"],
+                     floor=TOL_MIXED["floor"], report=report)
+    prod.check()
+    print(report)
+    pipe, fused = SalpBatch(n, prod.params, seed=4), SalpBatch(n, prod.params, seed=4)
+    pipe.reset(), fused.reset()
+    for t in range(2):
+        o1, r1, te1, tr1 = pipe.step(acts, auto_reset=True, pipeline=True)
+        o2, r2, te2, tr2 = fused.step(acts, auto_reset=True, pipeline=False)
+        np.testing.assert_array_equal(pipe.substeps, fused.substeps)
+        np.testing.assert_array_equal(te1, te2)
+        np.testing.assert_array_equal(tr1, tr2)
+        np.testing.assert_allclose(o1, o2, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(r1, r2, rtol=1e-5, atol=2e-4)
+
+
 def test_other_obstacle_count_and_masked_device_reset():
     import torch
     g = load_golden("ref_random.npz")
