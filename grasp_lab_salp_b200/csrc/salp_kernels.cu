@@ -144,18 +144,8 @@ int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& i
     salp_launch_step_f64(p, v, io, flags, order, stream);     // salp_step_f64.cu (compiled with -fmad=false)
   else if (p.randomization != 0)       // default-off robustness switches: separate instantiation
     salp_step_kernel_lat<SALP_PRECISION_MIXED_RANDOMIZED><<<grid_for(v.n, 32), 32, lat_tile_bytes(p), stream>>>(p, make_derived(p), v, io, flags, order);
-  else if (block == 32) {
-    static int variant = -1;
-    if (variant < 0) { const char* e = getenv("SALP_LAT_VARIANT"); variant = e ? atoi(e) : 0; }
-    if (variant == 200)
-      salp_step_kernel_lat200<SALP_PRECISION_MIXED><<<grid_for(v.n, 32), 32, lat_tile_bytes(p), stream>>>(p, make_derived(p), v, io, flags, order);
-    else if (variant == 184)
-      salp_step_kernel_lat184<SALP_PRECISION_MIXED><<<grid_for(v.n, 32), 32, lat_tile_bytes(p), stream>>>(p, make_derived(p), v, io, flags, order);
-    else if (variant == 168)
-      salp_step_kernel_lat168<SALP_PRECISION_MIXED><<<grid_for(v.n, 32), 32, lat_tile_bytes(p), stream>>>(p, make_derived(p), v, io, flags, order);
-    else
-      salp_step_kernel_lat<SALP_PRECISION_MIXED><<<grid_for(v.n, 32), 32, lat_tile_bytes(p), stream>>>(p, make_derived(p), v, io, flags, order);
-  }
+  else if (block == 32)
+    salp_step_kernel_lat<SALP_PRECISION_MIXED><<<grid_for(v.n, 32), 32, lat_tile_bytes(p), stream>>>(p, make_derived(p), v, io, flags, order);
   else
     salp_step_kernel<SALP_PRECISION_MIXED><<<grid_for(v.n, block), block, 0, stream>>>(p, make_derived(p), v, io, flags, order);
   SALP_LAUNCH_CHECK();

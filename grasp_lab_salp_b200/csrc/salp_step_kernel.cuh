@@ -16,8 +16,10 @@
 // io.terminal_obs back -- which lets salp_step_host hand it MAPPED HOST pointers (the results then
 // cross PCIe as each warp finishes, overlapped with the warps still integrating).
 template <int PREC>
-__device__ __forceinline__ void salp_step_lat_body(const SalpParams& p, const SalpDerived& dv, const SalpView& v,
-                                                   const SalpStepIO& io, uint32_t flags, const int32_t* __restrict__ order) {
+__global__ void __launch_bounds__(32, 1)
+salp_step_kernel_lat(const __grid_constant__ SalpParams p, const __grid_constant__ SalpDerived dv,
+                     const __grid_constant__ SalpView v, const __grid_constant__ SalpStepIO io, uint32_t flags,
+                     const int32_t* __restrict__ order) {
   extern __shared__ float tile[];
   const int D = SALP_OBS_BASE + 2 * p.num_obstacles;
   const int lane = threadIdx.x;
@@ -37,35 +39,6 @@ __device__ __forceinline__ void salp_step_lat_body(const SalpParams& p, const Sa
       if (tobs_row) io.terminal_obs[e * D + k] = tile[32 * D + j];
     }
   }
-}
-template <int PREC>
-__global__ void __launch_bounds__(32, 1)
-salp_step_kernel_lat(const __grid_constant__ SalpParams p, const __grid_constant__ SalpDerived dv,
-                     const __grid_constant__ SalpView v, const __grid_constant__ SalpStepIO io, uint32_t flags,
-                     const int32_t* __restrict__ order) {
-  salp_step_lat_body<PREC>(p, dv, v, io, flags, order);
-}
-// experiment: the same body under tighter register budgets (more resident warps per SM)
-template <int PREC>
-__global__ void __maxnreg__(200)
-salp_step_kernel_lat200(const __grid_constant__ SalpParams p, const __grid_constant__ SalpDerived dv,
-                        const __grid_constant__ SalpView v, const __grid_constant__ SalpStepIO io, uint32_t flags,
-                        const int32_t* __restrict__ order) {
-  salp_step_lat_body<PREC>(p, dv, v, io, flags, order);
-}
-template <int PREC>
-__global__ void __maxnreg__(184)
-salp_step_kernel_lat184(const __grid_constant__ SalpParams p, const __grid_constant__ SalpDerived dv,
-                        const __grid_constant__ SalpView v, const __grid_constant__ SalpStepIO io, uint32_t flags,
-                        const int32_t* __restrict__ order) {
-  salp_step_lat_body<PREC>(p, dv, v, io, flags, order);
-}
-template <int PREC>
-__global__ void __maxnreg__(168)
-salp_step_kernel_lat168(const __grid_constant__ SalpParams p, const __grid_constant__ SalpDerived dv,
-                        const __grid_constant__ SalpView v, const __grid_constant__ SalpStepIO io, uint32_t flags,
-                        const int32_t* __restrict__ order) {
-  salp_step_lat_body<PREC>(p, dv, v, io, flags, order);
 }
 
 template <int PREC>
