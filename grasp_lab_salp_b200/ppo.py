@@ -429,29 +429,35 @@ class RecurrentPPO(PPO):
     def __init__(self, env, config: PPOConfig | None = None, policy: LstmPolicy | None = None):
         cfg = config or PPOConfig(n_steps=32, batch_size=32 * 512)
         super().__init__(env, cfg, policy or LstmPolicy(env.obs_dim, 3, hidden=cfg.hidden))
+        self.graph_update = False            # the BPTT update stays eager (minibatches of env sequences)
         self.state = self.policy.initial_state(env.num_envs, self.device)
         self.starts = torch.ones(env.num_envs, dtype=torch.bool, device=self.device)
 
-    def collect(self):
-        cfg, env, T, N = self.cfg, self.env, self.cfg.n_steps, self.env.num_envs
-        dev = self.device
-        obs_buf = torch.empty((T, N, env.obs_dim), device=dev)
-        act_buf = torch.empty((T, N, 3), device=dev)
-        logp_buf = torch.empty((T, N), device=dev)
-        val_buf = torch.empty((T, N), device=dev)
-        rew_buf = torch.empty((T, N), device=dev)
-        done_buf = torch.empty((T, N), dtype=torch.bool, device=dev)
-        start_buf = torch.empty((T, N), dtype=torch.bool, device=dev)
-        init_state = tuple(s.clone() for s in self.state)
-        ep = torch.zeros(4, dtype=torch.float64, device=dev)
-        std = self.policy.log_std.exp()
+    def _alloc_rollout(self):
+        super()._alloc_rollout()
+        T, N, dev = self.cfg.n_steps, self.env.num_envs, self.device
+        self._rb["starts"] = torch.empty((T, N), dtype=torch.bool, device=dev)
+        self._rb["init_state"] = tuple(torch.empty_like(s) for s in self.state)
+
+    def _rollout_body(self):
+        """As PPO._rollout_body, carrying the per-env LSTM state in place (reset at episode starts);
+        capturable as one CUDA graph: both LSTM cells, the heads, salp_step and the bookkeeping of
+        all T steps."""
+        cfg, env, T, rb = self.cfg, self.env, self.cfg.n_steps, self._rb
+        for dst, src in zip(rb["init_state"], self.state):
+            dst.copy_(src)
+        ep = rb["ep"]
+        ep.zero_()
         for t in range(T):
             with torch.no_grad():
-                mean, v, self.state = self.policy.step(self.obs, self.state, self.starts)
-                noise = torch.randn(mean.shape, device=dev, generator=self.gen)
-                a = mean + noise * std
+                mean, v, new_state = self.policy.step(self.obs, self.state, self.starts)
+                for dst, src in zip(self.state, new_state):
+                    dst.copy_(src)
+                noise = torch.randn(mean.shape, device=self.device, generator=self.gen)
+                a = mean + noise * self.policy.log_std.exp()
                 logp = (-0.5 * noise.pow(2) - self.policy.log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
-            obs_buf[t], act_buf[t], logp_buf[t], val_buf[t], start_buf[t] = self.obs, a, logp, v, self.starts
+            rb["obs"][t].copy_(self.obs); rb["act"][t].copy_(a); rb["logp"][t].copy_(logp); rb["val"][t].copy_(v)
+            rb["starts"][t].copy_(self.starts)
             clipped = torch.minimum(torch.maximum(a, self.low), self.high).float().contiguous()
             obs, rew, term, trunc, term_obs = env.step_t(clipped)
             done = term | trunc
@@ -461,7 +467,7 @@ class RecurrentPPO(PPO):
             rew = torch.nan_to_num(rew, nan=0.0, posinf=0.0, neginf=0.0)
             if cfg.reward_clip > 0:
                 rew = rew.clamp(-cfg.reward_clip, cfg.reward_clip)
-            rew_buf[t], done_buf[t] = rew, done
+            rb["rew"][t].copy_(rew); rb["done"][t].copy_(done)
             self._ep_ret += rew
             self._ep_len += 1
             d = done.to(torch.float64)
@@ -470,14 +476,33 @@ class RecurrentPPO(PPO):
             keep = (~done).float()
             self._ep_ret *= keep
             self._ep_len *= keep
-            self.obs = obs.clone()
-            self.starts = done.clone()
+            self.obs.copy_(obs)
+            self.starts.copy_(done)
         with torch.no_grad():
             _, last_value, _ = self.policy.step(self.obs, self.state, self.starts)
-        adv, ret = compute_gae(rew_buf, val_buf, done_buf, last_value, cfg.gamma, cfg.gae_lambda)
-        self.env_steps += T * N
-        return dict(obs=obs_buf, act=act_buf, logp=logp_buf, val=val_buf, adv=adv, ret=ret, starts=start_buf,
-                    init_state=init_state, mean_reward=rew_buf.mean(), episodes=ep)
+        adv, ret = compute_gae(rb["rew"], rb["val"], rb["done"], last_value, cfg.gamma, cfg.gae_lambda)
+        rb["adv"].copy_(adv); rb["ret"].copy_(ret)
+        rb["mean_reward"].copy_(rb["rew"].mean())
+
+    def collect(self):
+        """Rollout buffers keep their [T, envs] shape (the update replays env sequences)."""
+        if not hasattr(self, "_rb"):
+            self._alloc_rollout()
+        self._roll_calls += 1
+        if self.use_graphs and self._roll_calls >= 2:
+            if self._roll_graph is None:          # the first rollout ran eagerly (warm-up); capture now
+                g = torch.cuda.CUDAGraph()
+                g.register_generator_state(self.gen)
+                with torch.cuda.graph(g):
+                    self._rollout_body()
+                self._roll_graph = g
+            self._roll_graph.replay()
+        else:
+            self._rollout_body()
+        self.env_steps += self.cfg.n_steps * self.env.num_envs
+        rb = self._rb
+        return dict(obs=rb["obs"], act=rb["act"], logp=rb["logp"], val=rb["val"], adv=rb["adv"], ret=rb["ret"],
+                    starts=rb["starts"], init_state=rb["init_state"], mean_reward=rb["mean_reward"], episodes=rb["ep"])
 
     def update(self, roll):
         cfg = self.cfg
