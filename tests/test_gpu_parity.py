@@ -290,6 +290,29 @@ def test_pipeline_kernel_matches_fused_kernel():
     fused.check()
 
 
+def test_pipeline_kernel_is_deterministic_at_full_size():
+    """Two handles, same seed, same actions, BASELINE's 4096 envs (every SM busy with one
+    three-warp block), 40 free-running steps: bit-identical outputs and state.  A missed hand-off
+    between the producer and consumer warps (a shared-memory race) would show up here as a
+    run-to-run difference."""
+    from grasp_lab_salp_b200.params import FIELDS
+    n, T = 4096, 40
+    g = load_golden("ref_random.npz")
+    acts = uniform_actions(np.random.default_rng(77), T, n)
+    a, b = SalpBatch(n, golden_params(g), seed=5), SalpBatch(n, golden_params(g), seed=5)
+    np.testing.assert_array_equal(a.reset(), b.reset())
+    for t in range(T):
+        ra = a.step(acts[t], auto_reset=True, pipeline=True)
+        rb = b.step(acts[t], auto_reset=True, pipeline=True)
+        for x, y in zip(ra, rb):
+            np.testing.assert_array_equal(x, y)
+        np.testing.assert_array_equal(a.substeps, b.substeps)
+    for col in FIELDS:
+        np.testing.assert_array_equal(a.get_state(col), b.get_state(col), err_msg=col)
+    a.check()
+    b.check()
+
+
 def test_pipeline_kernel_short_cycles_and_chunk_boundaries():
     """Cycles of K = 0, 1, 2, ... substeps (contraction 0, coast chosen so that total = K * dt) put
     the end of the cycle on every position of the pipeline kernel's 8-substep hand-off chunks and
