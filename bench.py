@@ -438,7 +438,8 @@ def run_cuda_arm(args):
                          "peak_source": ("measured in this run: salp_probe_fp32_peak (FFMA, 2048 thr/SM)"
                                          if fp32_peak else "nominal"),
                          "nominal_peak": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved_tf / NOMINAL_FP32_TFLOPS,
-                         "flop_per_substep": FLOP_PER_SUBSTEP, "kernel": "salp_step_kernel_lat<MIXED>" if prec == PRECISION_MIXED else "salp_step_kernel<F64>",
+                         "flop_per_substep": FLOP_PER_SUBSTEP, "kernel": ("salp_step_kernel<F64>" if prec != PRECISION_MIXED else
+                                    "salp_step_kernel_pipe" if n <= 32 * 148 and not sort_flag(n) else "salp_step_kernel_lat<MIXED>"),
                          "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": hbm_achieved / hbm_peak, "bytes_per_env_step": bytes_per_env_step,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
