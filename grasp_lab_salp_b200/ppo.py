@@ -317,10 +317,14 @@ class PPO:
             stats += torch.stack([((lr.exp() - 1) - lr).mean(), ((ratio - 1).abs() > cfg.clip_range).float().mean(),
                                   value_loss.detach(), policy_loss.detach()])
 
+    def _update_domain(self, roll):
+        """(number of items a minibatch is drawn from, items per minibatch): samples for the MLP policy."""
+        n = roll["obs"].shape[0]
+        return n, min(self.cfg.batch_size, n)
+
     def update(self, roll):
         cfg = self.cfg
-        n = roll["obs"].shape[0]
-        bs = min(cfg.batch_size, n)
+        n, bs = self._update_domain(roll)
         stats = getattr(self, "_upd_stats", None)
         if stats is None:
             stats = self._upd_stats = torch.zeros(4, device=self.device)
@@ -429,7 +433,6 @@ class RecurrentPPO(PPO):
     def __init__(self, env, config: PPOConfig | None = None, policy: LstmPolicy | None = None):
         cfg = config or PPOConfig(n_steps=32, batch_size=32 * 512)
         super().__init__(env, cfg, policy or LstmPolicy(env.obs_dim, 3, hidden=cfg.hidden))
-        self.graph_update = False            # the BPTT update stays eager (minibatches of env sequences)
         self.state = self.policy.initial_state(env.num_envs, self.device)
         self.starts = torch.ones(env.num_envs, dtype=torch.bool, device=self.device)
 
@@ -504,44 +507,43 @@ class RecurrentPPO(PPO):
         return dict(obs=rb["obs"], act=rb["act"], logp=rb["logp"], val=rb["val"], adv=rb["adv"], ret=rb["ret"],
                     starts=rb["starts"], init_state=rb["init_state"], mean_reward=rb["mean_reward"], episodes=rb["ep"])
 
-    def update(self, roll):
-        cfg = self.cfg
+    def _update_domain(self, roll):
+        """Minibatches are subsets of ENVS: whole [T] sequences, batch_size // T of them."""
         T, N = roll["logp"].shape
-        envs_per_mb = max(1, min(N, cfg.batch_size // T))
-        kl = clipf = vl = pl = 0.0
-        count = 0
-        for _ in range(cfg.n_epochs):
-            perm = torch.randperm(N, device=self.device, generator=self.gen)
-            for s in range(0, N - envs_per_mb + 1, envs_per_mb):
-                idx = perm[s:s + envs_per_mb]
-                state = tuple(x[idx] for x in roll["init_state"])
-                means, vals = [], []
-                for t in range(T):                         # BPTT over the rollout, reset at episode starts
-                    m, v, state = self.policy.step(roll["obs"][t, idx], state, roll["starts"][t, idx])
-                    means.append(m)
-                    vals.append(v)
-                mean, val = torch.stack(means), torch.stack(vals)
-                dist = torch.distributions.Normal(mean, self.policy.log_std.exp(), validate_args=False)
-                logp = dist.log_prob(roll["act"][:, idx]).sum(-1)
-                old_logp = roll["logp"][:, idx]
-                adv = roll["adv"][:, idx]
-                if cfg.normalize_advantage:
-                    adv = (adv - adv.mean()) / (adv.std() + 1e-8)
-                ratio = (logp - old_logp).exp()
-                policy_loss = -torch.minimum(adv * ratio, adv * ratio.clamp(1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
-                value_loss = (roll["ret"][:, idx] - val).pow(2).mean()
-                loss = policy_loss + cfg.vf_coef * value_loss - cfg.ent_coef * dist.entropy().sum(-1).mean()
-                self.opt.zero_grad(set_to_none=True)
-                loss.backward()
-                self._allreduce_grads()
-                nn.utils.clip_grad_norm_(self.policy.parameters(), cfg.max_grad_norm)
-                self.opt.step()
-                with torch.no_grad():
-                    lr = logp - old_logp
-                    kl += float(((lr.exp() - 1) - lr).mean())
-                    clipf += float(((ratio - 1).abs() > cfg.clip_range).float().mean())
-                    vl += float(value_loss)
-                    pl += float(policy_loss)
-                count += 1
-        c = max(count, 1)
-        return dict(approx_kl=kl / c, clip_fraction=clipf / c, value_loss=vl / c, policy_loss=pl / c)
+        return N, max(1, min(N, self.cfg.batch_size // T))
+
+    def _minibatch_step(self, roll, idx, stats):
+        """One optimiser step on the env sequences `idx`: BPTT over the rollout from the stored
+        initial LSTM state, hidden state reset at episode starts.  No host synchronisation, so it
+        can be captured and replayed as a CUDA graph like the MLP step."""
+        cfg = self.cfg
+        T = roll["logp"].shape[0]
+        state = tuple(x[idx] for x in roll["init_state"])
+        obs, starts = roll["obs"][:, idx], roll["starts"][:, idx]
+        means, vals = [], []
+        for t in range(T):
+            m, v, state = self.policy.step(obs[t], state, starts[t])
+            means.append(m)
+            vals.append(v)
+        mean, val = torch.stack(means), torch.stack(vals)
+        log_std = self.policy.log_std
+        z = (roll["act"][:, idx] - mean) * (-log_std).exp()
+        logp = (-0.5 * z.pow(2) - log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
+        entropy = (0.5 + 0.5 * math.log(2 * math.pi) + log_std).sum()
+        old_logp = roll["logp"][:, idx]
+        adv = roll["adv"][:, idx]
+        if cfg.normalize_advantage:
+            adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+        ratio = (logp - old_logp).exp()
+        policy_loss = -torch.minimum(adv * ratio, adv * ratio.clamp(1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
+        value_loss = (roll["ret"][:, idx] - val).pow(2).mean()
+        loss = policy_loss + cfg.vf_coef * value_loss - cfg.ent_coef * entropy
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        self._allreduce_grads()
+        nn.utils.clip_grad_norm_(self.policy.parameters(), cfg.max_grad_norm)
+        self.opt.step()
+        with torch.no_grad():
+            lr = logp - old_logp
+            stats += torch.stack([((lr.exp() - 1) - lr).mean(), ((ratio - 1).abs() > cfg.clip_range).float().mean(),
+                                  value_loss.detach(), policy_loss.detach()])
