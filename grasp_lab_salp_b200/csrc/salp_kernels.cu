@@ -123,18 +123,20 @@ int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& i
     order = scratch.order;
   }
   const int block = block_for(v.n);
-  // batches that fit one 2-warp block per SM: the shape-producer / motion-consumer pipeline
+  // batches that fit one three-warp block per SM: the producer / consumer pipeline
   // (salp_pipe_kernel.cuh), unless SALP_STEP_FUSED asks for the one-warp kernel
   if (p.precision == SALP_PRECISION_MIXED && p.randomization == 0 && !order && !(flags & SALP_STEP_FUSED) &&
       v.n <= (int64_t)32 * (v.sm_count > 0 ? v.sm_count : 148)) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};              // per device: the opt-in is a per-device function attribute
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
       SalpParams widest = p;
       widest.num_obstacles = SALP_MAX_OBSTACLES;
       if (cudaFuncSetAttribute(salp_step_kernel_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)pipe_smem_bytes(widest)) != cudaSuccess)
         return SALP_ERR_CUDA;
-      configured = true;
+      if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     salp_step_kernel_pipe<<<grid_for(v.n, 32), SALP_PIPE_THREADS, pipe_smem_bytes(p), stream>>>(p, make_derived(p), v, io, flags);
     SALP_LAUNCH_CHECK();
