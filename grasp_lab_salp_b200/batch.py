@@ -56,6 +56,9 @@ class SalpBatch:
         self.substeps = self.host_buffer((n,), np.int32)
         self.metrics = self.host_buffer((n, NUM_EPISODE_METRICS), np.float64)
         self._io_host = _lib.SalpStepIO()
+        self._io_host_extras = None
+        self._io_host_ref = None
+        self._io_host_bufs = (None,) * 5
         self._dev = None          # lazily created torch output tensors of the device face
 
     def host_buffer(self, shape, dtype) -> np.ndarray:
@@ -128,22 +131,32 @@ class SalpBatch:
 
     def step(self, actions, auto_reset: bool = False, sort_by_k: bool = False, extras: bool = True,
              pipeline=None):
-        a = np.ascontiguousarray(actions, np.float32)
+        a = actions
+        if not (type(a) is np.ndarray and a.dtype == np.float32 and a.flags.c_contiguous):
+            a = np.ascontiguousarray(actions, np.float32)
         if a.shape != (self.num_envs, 3):
             raise ValueError(f"actions must have shape [{self.num_envs}, 3]")
         io = self._io_host
-        io.actions = a.ctypes.data
-        io.obs = self.obs.ctypes.data
-        io.reward = self.reward.ctypes.data
-        io.terminated = self.terminated.ctypes.data
-        io.truncated = self.truncated.ctypes.data
-        io.terminal_obs = self.terminal_obs.ctypes.data
-        io.reward_terms = self.terms.ctypes.data if extras else None
-        io.substeps = self.substeps.ctypes.data if extras else None
-        io.episode_metrics = self.metrics.ctypes.data if extras else None
+        bufs = (self.obs, self.reward, self.terminated, self.truncated, self.terminal_obs)
+        if self._io_host_extras is not extras or any(x is not y for x, y in zip(bufs, self._io_host_bufs)):
+            # (output pointers only change with `extras` or when a caller swaps in its own arrays)
+            self._io_host_bufs = bufs
+            io.obs = self.obs.ctypes.data
+            io.reward = self.reward.ctypes.data
+            io.terminated = self.terminated.ctypes.data
+            io.truncated = self.truncated.ctypes.data
+            io.terminal_obs = self.terminal_obs.ctypes.data
+            io.reward_terms = self.terms.ctypes.data if extras else None
+            io.substeps = self.substeps.ctypes.data if extras else None
+            io.episode_metrics = self.metrics.ctypes.data if extras else None
+            self._io_host_extras = extras
+            self._io_host_ref = C.byref(io)
+        io.actions = a.__array_interface__["data"][0]
         flags = ((STEP_AUTORESET if auto_reset else 0) | (STEP_SORT_BY_K if sort_by_k else 0)
                  | (0 if pipeline is None else (STEP_PIPELINE if pipeline else STEP_FUSED)))
-        self._check(self._L.salp_step_host(self._h, C.byref(io), flags))
+        rc = self._L.salp_step_host(self._h, self._io_host_ref, flags)
+        if rc != 0:
+            self._check(rc)
         return self.obs, self.reward, self.terminated, self.truncated
 
     def get_state(self, name: str) -> np.ndarray:
