@@ -293,7 +293,7 @@ struct Motion32 {
 };
 
 // _newton_equations + _euler_equations + the velocity half of _update_motion_states
-// (robot.py:789-862) in the pre-divided form documented at Coef32.  ~80 FP32 instructions.
+// (robot.py:789-862) in the pre-divided form documented at Coef32.  ~85 FP32 instructions.
 // OUDisturbance.sample() for the three live components (robot.py:236-242): Euler-Maruyama step
 // x += theta (0 - x) dt + sigma sqrt(dt) N(0, 1), theta = 2, sigma = 0.05 (force) / 0.01 (torque)
 SALP_HD void ou_step(const SalpDerived& dv, RandCtx& rc, int k) {
@@ -359,7 +359,7 @@ SALP_HD void dyn_step(const SalpDerived& dv, const Coef32& g, Motion32& s, RandC
 
 // The kinematic half of _update_motion_states (robot.py:864-875): Euler-angle rates at the old
 // roll/pitch (dynamics.py:21-31), new angles, body->world rotation Rz Ry Rx (dynamics.py:35-58) by
-// successive elementary rotations, the three position/angle integrals.  ~65 FP32 instructions.
+// successive elementary rotations, the three position/angle integrals.  ~70 FP32 instructions.
 // v, w are the velocities AFTER dyn_step of the same substep.
 // (sin, cos)(x) -> (sin, cos)(x + d).  The Taylor kernels are valid for |d| <= 0.55 (a substep moves an
 // Euler angle by ~1e-2 rad); a tumbling body passing the pitch = +-pi/2 singularity of the Euler-rate

@@ -2,9 +2,9 @@
 //
 // With a few thousand envs the GPU is almost empty (4096 envs = 128 warps on 592 SM sub-partitions)
 // and the step time is K_max (~1340 substeps of the slowest env) x the time ONE warp needs per
-// substep -- and that warp is bound by instruction issue: ~340 instructions per substep while the
+// substep -- and that warp is bound by instruction issue: ~330 instructions per substep while the
 // body shape moves (kinematics + dynamics + the fp64 shape chain and its ~90-instruction
-// coefficient set), 166 afterwards.  But the shape and every coefficient derived from it depend on
+// coefficient set), ~150 afterwards.  But the shape and every coefficient derived from it depend on
 // the action and the substep index only, never on the motion state.  So one block of THREE warps
 // owns 32 envs, each warp on its own SM sub-partition:
 //   * warp 2 (front)    : shape_front(j), j = 1..W -- the fp64 shape chain and its backward
