@@ -62,6 +62,27 @@ def main():
     print("warp-stall sampling (share of samples):")
     for s, c in stalls.most_common(8):
         print(f"   {s:26s} {c / tot_samp:6.3f}")
+    # hot loops: maximal runs of consecutive SASS lines with the same execution count
+    regions, cur = [], None
+    for i, r in enumerate(data):
+        k = int(r[ix["Instructions Executed"]])
+        if cur is not None and cur["count"] == k:
+            cur["end"] = i
+        else:
+            cur = dict(count=k, start=i, end=i, samples=0, st=collections.Counter())
+            regions.append(cur)
+        cur["samples"] += int(r[ix["# Samples"]])
+        for c in scols:
+            cur["st"][c] += int(r[ix[c]] or 0)
+    regions = [g for g in regions if g["count"] > 0 and g["end"] - g["start"] >= 40]
+    regions.sort(key=lambda g: -g["count"] * (g["end"] - g["start"] + 1))
+    print("\nhot loops (runs of SASS lines with one execution count; share of executed warp-instructions):")
+    for g in regions[:6]:
+        n = g["end"] - g["start"] + 1
+        tot = sum(g["st"].values()) or 1
+        top = ", ".join(f"{k[6:]} {v / tot:.2f}" for k, v in g["st"].most_common(4))
+        print(f"   {n:4d} instructions x {g['count']:9d} executions = {n * g['count'] / tot_inst:5.3f}; "
+              f"samples {g['samples'] / tot_samp:5.3f} of all ({top}); first: {data[g['start']][ix['Source']].strip()[:40]}")
 
 
 if __name__ == "__main__":
