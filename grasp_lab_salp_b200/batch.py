@@ -21,7 +21,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .params import (NUM_EPISODE_METRICS, NUM_REWARD_TERMS, STEP_AUTORESET, STEP_FUSED, STEP_PIPELINE, STEP_SORT_BY_K, SalpParams,
+from .params import (NUM_EPISODE_METRICS, NUM_REWARD_TERMS, STEP_AUTORESET, STEP_FUSED, STEP_GENERIC, STEP_PIPELINE, STEP_SORT_BY_K, SalpParams,
                      default_params, field_dtype, field_id)
 
 
@@ -130,7 +130,7 @@ class SalpBatch:
         return self.obs
 
     def step(self, actions, auto_reset: bool = False, sort_by_k: bool = False, extras: bool = True,
-             pipeline=None):
+             pipeline=None, generic: bool = False):
         a = actions
         if not (type(a) is np.ndarray and a.dtype == np.float32 and a.flags.c_contiguous):
             a = np.ascontiguousarray(actions, np.float32)
@@ -153,7 +153,8 @@ class SalpBatch:
             self._io_host_ref = C.byref(io)
         io.actions = a.__array_interface__["data"][0]
         flags = ((STEP_AUTORESET if auto_reset else 0) | (STEP_SORT_BY_K if sort_by_k else 0)
-                 | (0 if pipeline is None else (STEP_PIPELINE if pipeline else STEP_FUSED)))
+                 | (0 if pipeline is None else (STEP_PIPELINE if pipeline else STEP_FUSED))
+                 | (STEP_GENERIC if generic else 0))
         rc = self._L.salp_step_host(self._h, self._io_host_ref, flags)
         if rc != 0:
             self._check(rc)
@@ -226,7 +227,7 @@ class SalpBatch:
         return bufs["obs"]
 
     def step_device(self, actions, auto_reset: bool = True, sort_by_k: bool = False, extras: bool = False,
-                    pipeline=None):
+                    pipeline=None, generic: bool = False):
         """actions: float32 CUDA tensor [N,3] on this batch's device.  Asynchronous on the current
         torch stream.  Returns (obs, reward, terminated, truncated) device tensors (reused every
         call); ``self.dev["terminal_obs"]`` etc. hold the rest."""
@@ -246,7 +247,8 @@ class SalpBatch:
         io.reward_terms = bufs["terms"].data_ptr() if extras else None
         io.episode_metrics = bufs["metrics"].data_ptr() if extras else None
         flags = ((STEP_AUTORESET if auto_reset else 0) | (STEP_SORT_BY_K if sort_by_k else 0)
-                 | (0 if pipeline is None else (STEP_PIPELINE if pipeline else STEP_FUSED)))
+                 | (0 if pipeline is None else (STEP_PIPELINE if pipeline else STEP_FUSED))
+                 | (STEP_GENERIC if generic else 0))
         self._check(self._L.salp_step(self._h, C.byref(io), flags, self._stream_ptr(self.device)))
         return bufs["obs"], bufs["reward"], bufs["terminated"], bufs["truncated"]
 

@@ -112,6 +112,8 @@ int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& i
                      const SalpScratch& scratch, cudaStream_t stream) {
   int launches = 0;
   const int32_t* order = nullptr;
+  SalpDerived dv = make_derived(p);
+  if (flags & SALP_STEP_GENERIC) dv.axisym = 0;      // the general form of the loop even for axisymmetric coefficient sets
   if (flags & SALP_STEP_SORT_BY_K) {
     if (cudaMemsetAsync(scratch.hist, 0, sizeof(int32_t) * SALP_SORT_BINS, stream) != cudaSuccess)
       return SALP_ERR_CUDA;
@@ -138,18 +140,18 @@ int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& i
         return SALP_ERR_CUDA;
       if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    salp_step_kernel_pipe<<<grid_for(v.n, 32), SALP_PIPE_THREADS, pipe_smem_bytes(p), stream>>>(p, make_derived(p), v, io, flags);
+    salp_step_kernel_pipe<<<grid_for(v.n, 32), SALP_PIPE_THREADS, pipe_smem_bytes(p), stream>>>(p, dv, v, io, flags);
     SALP_LAUNCH_CHECK();
     return launches + 1;
   }
   if (p.precision == SALP_PRECISION_F64)
     salp_launch_step_f64(p, v, io, flags, order, stream);     // salp_step_f64.cu (compiled with -fmad=false)
   else if (p.randomization != 0)       // default-off robustness switches: separate instantiation
-    salp_step_kernel_lat<SALP_PRECISION_MIXED_RANDOMIZED><<<grid_for(v.n, 32), 32, lat_tile_bytes(p), stream>>>(p, make_derived(p), v, io, flags, order);
+    salp_step_kernel_lat<SALP_PRECISION_MIXED_RANDOMIZED><<<grid_for(v.n, 32), 32, lat_tile_bytes(p), stream>>>(p, dv, v, io, flags, order);
   else if (block == 32)
-    salp_step_kernel_lat<SALP_PRECISION_MIXED><<<grid_for(v.n, 32), 32, lat_tile_bytes(p), stream>>>(p, make_derived(p), v, io, flags, order);
+    salp_step_kernel_lat<SALP_PRECISION_MIXED><<<grid_for(v.n, 32), 32, lat_tile_bytes(p), stream>>>(p, dv, v, io, flags, order);
   else
-    salp_step_kernel<SALP_PRECISION_MIXED><<<grid_for(v.n, block), block, 0, stream>>>(p, make_derived(p), v, io, flags, order);
+    salp_step_kernel<SALP_PRECISION_MIXED><<<grid_for(v.n, block), block, 0, stream>>>(p, dv, v, io, flags, order);
   SALP_LAUNCH_CHECK();
   return launches + 1;
 }

@@ -91,6 +91,10 @@ struct SalpDerived {
   float init_length_f, init_width_f, jet_gain_f, rho_f, m_base_f, four_thirds_pi_f, skin3_f, c2_f, c1_f, c0_f;   // fp32 shape (never differenced)
   float Ca[3], E[3], Cat[3], Car[3], CaD[3], CatF[3];
   float thi[3], tspan[3], rhi[3], rspan[3];
+  // 1 if axes 1 and 2 carry the same coefficients (the default parameters do): the loop then
+  // shares their coefficient entries and drops the terms whose coefficient is identically 0
+  // (bit-identical results; see make_coefs / dyn_step)
+  int axisym;
 };
 
 SALP_HD SalpDerived make_derived(const SalpParams& p) {
@@ -150,6 +154,8 @@ SALP_HD SalpDerived make_derived(const SalpParams& p) {
     k.rhi[i] = (float)p.rot_drag_range[2 * i + 1];
     k.rspan[i] = (float)(p.rot_drag_range[2 * i + 1] - p.rot_drag_range[2 * i]);
   }
+  k.axisym = k.Ca[1] == k.Ca[2] && k.Cat[1] == k.Cat[2] && k.Car[0] == k.Car[1] && k.Car[1] == k.Car[2] &&
+             k.thi[1] == k.thi[2] && k.tspan[1] == k.tspan[2] && k.rhi[1] == k.rhi[2] && k.rspan[1] == k.rspan[2];
   return k;
 }
 
@@ -226,6 +232,9 @@ SALP_HD void shape64_step(const SalpParams& p, const SalpDerived& k, double lh, 
 // All fp32 coefficients of the coming substep.  Mass, inertia, areas and drag coefficients are
 // evaluated in fp32 from the half-length / half-width (they are never differenced); the
 // differenced quantities arrive from the fp64 chain already rounded.
+// AXI (SalpDerived.axisym): entries [2] of kdm / kqI / klI equal entries [1], mrm[1] = mrm[2] = mrm[0],
+// JdI[0] = AdI[0] = 0, JdI[2] = -JdI[1], AdI[2] = -AdI[1] -- they are neither computed nor read.
+template <bool AXI = false>
 SALP_HD void make_coefs(const SalpDerived& k, const float dir[3], bool jet_on, float lh, float wh,
                         float I_rate0, float I_rate1, float dV_dt, float com, float com_rate, float com_acc,
                         Coef32& g) {
@@ -245,29 +254,39 @@ SALP_HD void make_coefs(const SalpDerived& k, const float dir[3], bool jet_on, f
   // -rho/2 * area_i (geometry.py:68-75: areas pi wh^2, pi lh wh, pi lh wh)
   const float P0 = k.half_rho_pi * wh2, P1 = k.half_rho_pi * lw;
   const float Q0 = P0 * inv_m, Q1 = P1 * inv_m;
-  const float ct0 = fmaf(-nr, k.tspan[0], k.thi[0]), ct1 = fmaf(-nr, k.tspan[1], k.thi[1]), ct2 = fmaf(-nr, k.tspan[2], k.thi[2]);
-  const float cr0 = fmaf(-nr, k.rspan[0], k.rhi[0]), cr1 = fmaf(-nr, k.rspan[1], k.rhi[1]), cr2 = fmaf(-nr, k.rspan[2], k.rhi[2]);
-  g.kdm[0] = Q0 * ct0; g.kdm[1] = Q1 * ct1; g.kdm[2] = Q1 * ct2;
+  const float ct0 = fmaf(-nr, k.tspan[0], k.thi[0]), ct1 = fmaf(-nr, k.tspan[1], k.thi[1]);
+  const float cr0 = fmaf(-nr, k.rspan[0], k.rhi[0]), cr1 = fmaf(-nr, k.rspan[1], k.rhi[1]);
+  g.kdm[0] = Q0 * ct0; g.kdm[1] = Q1 * ct1;
+  if (!AXI) g.kdm[2] = Q1 * fmaf(-nr, k.tspan[2], k.thi[2]);
   const float mr = (k.rho_f * dV_dt) * inv_m;                      // mass_rate / m   (geometry.py:98-101)
-  g.mrm[0] = mr * k.Car[0]; g.mrm[1] = mr * k.Car[1]; g.mrm[2] = mr * k.Car[2];
+  g.mrm[0] = mr * k.Car[0];
+  if (!AXI) { g.mrm[1] = mr * k.Car[1]; g.mrm[2] = mr * k.Car[2]; }
   const float f = jet_on ? k.jet_gain_f * dV_dt * dV_dt : 0.0f;
   const float fm = f * inv_m;
   g.aj[0] = dir[0] * fm; g.aj[1] = dir[1] * fm; g.aj[2] = dir[2] * fm;
-  const float kr0 = P0 * cr0, kr1 = P1 * cr1, kr2 = P1 * cr2;
+  const float kr0 = P0 * cr0, kr1 = P1 * cr1;
   // drag torque: dims = (width^3, length^3, length^3) = 8 (wh^3, lh^3, lh^3)
   const float E0 = (wh2 * wh) * (8.0f * inv_I0), E1 = (lh2 * lh) * (8.0f * inv_I1);
-  g.kqI[0] = kr0 * E0; g.kqI[1] = kr1 * E1; g.kqI[2] = kr2 * E1;
+  g.kqI[0] = kr0 * E0; g.kqI[1] = kr1 * E1;
   const float tw = k.torque_ratio * (wh + wh);
   g.klI[0] = fmaf(kr0, tw, -I_rate0) * inv_I0;
   g.klI[1] = fmaf(kr1, tw, -I_rate1) * inv_I1;
-  g.klI[2] = fmaf(kr2, tw, -I_rate1) * inv_I1;
+  if (!AXI) {
+    const float kr2 = P1 * fmaf(-nr, k.rspan[2], k.rhi[2]);
+    g.kqI[2] = kr2 * E1;
+    g.klI[2] = fmaf(kr2, tw, -I_rate1) * inv_I1;
+  }
   // (J_i2 - J_i1) / I_i with J = I o (1 + Cat), I = (I0, I1, I1)
   const float r01 = I0 * inv_I1;
-  g.JdI[0] = (I1 * inv_I0) * (k.CatF[2] - k.CatF[1]);
   g.JdI[1] = fmaf(r01, k.CatF[0], -k.CatF[2]);
-  g.JdI[2] = fmaf(-r01, k.CatF[0], k.CatF[1]);
-  const float mI0 = m * inv_I0, mI1 = m * inv_I1;
-  g.AdI[0] = mI0 * k.CaD[0]; g.AdI[1] = mI1 * k.CaD[1]; g.AdI[2] = mI1 * k.CaD[2];
+  const float mI1 = m * inv_I1;
+  g.AdI[1] = mI1 * k.CaD[1];
+  if (!AXI) {
+    g.JdI[0] = (I1 * inv_I0) * (k.CatF[2] - k.CatF[1]);
+    g.JdI[2] = fmaf(-r01, k.CatF[0], k.CatF[1]);
+    g.AdI[0] = (m * inv_I0) * k.CaD[0];
+    g.AdI[2] = mI1 * k.CaD[2];
+  }
   g.inv_m = inv_m;
   g.inv_Iz = inv_I1;
   const float afI = (k.arm0 - lh) * (f * inv_I1);                  // arm = (arm0 - lh, 0, 0)   robot.py:931-935
@@ -315,7 +334,7 @@ SALP_HD void ou_step(const SalpDerived& dv, RandCtx& rc, int k) {
 
 // STATIC: the shape has stopped moving (part B of the loop, after the warp-uniform end of every
 // lane's update window + its two settle substeps): com_rate and com_acc are exactly 0 there.
-template <bool NOISE = false, bool STATIC = false>
+template <bool NOISE = false, bool STATIC = false, bool AXI = false>
 SALP_HD void dyn_step(const SalpDerived& dv, const Coef32& g, Motion32& s, RandCtx* rc = nullptr, int k = 0) {
   const float v0 = s.v0, v1 = s.v1, v2 = s.v2, w0 = s.w0, w1 = s.w1, w2 = s.w2;
   float sd = fast_norm3(v0, v1, v2) + dv.ratio_f;               // |v| v + ratio v = v (|v| + ratio)
@@ -339,12 +358,22 @@ SALP_HD void dyn_step(const SalpDerived& dv, const Coef32& g, Motion32& s, RandC
     fict1 = fmaf(g.com, t1, rn::fmul(w2, g.com_rate2));
     fict2 = fmaf(g.com, t2, -rn::fmul(w1, g.com_rate2));
   }
-  float na0 = g.aj[0] + v0 * fmaf(g.kdm[0], sd, -g.mrm[0]) - dv.Ca[0] * s.ac0 - (w1 * ev2 - w2 * ev1) + fict0;
-  float na1 = g.aj[1] + v1 * fmaf(g.kdm[1], sd, -g.mrm[1]) - dv.Ca[1] * s.ac1 - (w2 * ev0 - w0 * ev2) + fict1;
-  float na2 = g.aj[2] + v2 * fmaf(g.kdm[2], sd, -g.mrm[2]) - dv.Ca[2] * s.ac2 - (w0 * ev1 - w1 * ev0) + fict2;
-  float nl0 = w0 * fmaf(g.kqI[0], wn, g.klI[0]) - dv.Cat[0] * s.al0 - p12 * g.JdI[0] - (v1 * v2) * g.AdI[0];
-  float nl1 = g.tj1 + w1 * fmaf(g.kqI[1], wn, g.klI[1]) - dv.Cat[1] * s.al1 - p20 * g.JdI[1] - (v2 * v0) * g.AdI[1];
-  float nl2 = g.tj2 + w2 * fmaf(g.kqI[2], wn, g.klI[2]) - dv.Cat[2] * s.al2 - p01 * g.JdI[2] - (v0 * v1) * g.AdI[2];
+  float na0, na1, na2, nl0, nl1, nl2;
+  if (AXI) {     // same values as below with kdm[2] = kdm[1], mrm[i] = mrm[0], JdI[0] = AdI[0] = 0, JdI[2] = -JdI[1], AdI[2] = -AdI[1]
+    na0 = g.aj[0] + v0 * fmaf(g.kdm[0], sd, -g.mrm[0]) - dv.Ca[0] * s.ac0 - (w1 * ev2 - w2 * ev1) + fict0;
+    na1 = g.aj[1] + v1 * fmaf(g.kdm[1], sd, -g.mrm[0]) - dv.Ca[1] * s.ac1 - (w2 * ev0 - w0 * ev2) + fict1;
+    na2 = g.aj[2] + v2 * fmaf(g.kdm[1], sd, -g.mrm[0]) - dv.Ca[2] * s.ac2 - (w0 * ev1 - w1 * ev0) + fict2;
+    nl0 = w0 * fmaf(g.kqI[0], wn, g.klI[0]) - dv.Cat[0] * s.al0;
+    nl1 = g.tj1 + w1 * fmaf(g.kqI[1], wn, g.klI[1]) - dv.Cat[1] * s.al1 - p20 * g.JdI[1] - (v2 * v0) * g.AdI[1];
+    nl2 = g.tj2 + w2 * fmaf(g.kqI[1], wn, g.klI[1]) - dv.Cat[2] * s.al2 + p01 * g.JdI[1] + (v0 * v1) * g.AdI[1];
+  } else {
+    na0 = g.aj[0] + v0 * fmaf(g.kdm[0], sd, -g.mrm[0]) - dv.Ca[0] * s.ac0 - (w1 * ev2 - w2 * ev1) + fict0;
+    na1 = g.aj[1] + v1 * fmaf(g.kdm[1], sd, -g.mrm[1]) - dv.Ca[1] * s.ac1 - (w2 * ev0 - w0 * ev2) + fict1;
+    na2 = g.aj[2] + v2 * fmaf(g.kdm[2], sd, -g.mrm[2]) - dv.Ca[2] * s.ac2 - (w0 * ev1 - w1 * ev0) + fict2;
+    nl0 = w0 * fmaf(g.kqI[0], wn, g.klI[0]) - dv.Cat[0] * s.al0 - p12 * g.JdI[0] - (v1 * v2) * g.AdI[0];
+    nl1 = g.tj1 + w1 * fmaf(g.kqI[1], wn, g.klI[1]) - dv.Cat[1] * s.al1 - p20 * g.JdI[1] - (v2 * v0) * g.AdI[1];
+    nl2 = g.tj2 + w2 * fmaf(g.kqI[2], wn, g.klI[2]) - dv.Cat[2] * s.al2 - p01 * g.JdI[2] - (v0 * v1) * g.AdI[2];
+  }
   if (NOISE) {        // force_noise / torque_noise join the sums of _newton_equations / _euler_equations
     ou_step(dv, *rc, k);
     na0 = fmaf(rc->ou_fx, g.inv_m, na0);
@@ -441,11 +470,13 @@ struct ShapeTrack {
 
 // update_state + update_properties after substep j-1 (robot.py:640-668), only called while the
 // shape moves or its backward differences have not been flushed yet.
+template <bool AXI = false>
 SALP_HD void shape_update_at(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c, double t,
                              const float dir[3], int j, int k_T0, int k_jet, ShapeTrack& st, Coef32& g);
+template <bool AXI = false>
 SALP_HD void shape_update(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c, const double* time_table,
                           const float dir[3], int j, int k_T0, int k_jet, ShapeTrack& st, Coef32& g) {
-  shape_update_at(p, dv, c, time_table[j], dir, j, k_T0, k_jet, st, g);
+  shape_update_at<AXI>(p, dv, c, time_table[j], dir, j, k_T0, k_jet, st, g);
 }
 // The update in two stages, so that the pipeline kernel can run them on different warps:
 //   shape_front : fp64 -- shape at t_j, the differenced quantities, rounded to fp32 once  (ShapeFront)
@@ -483,19 +514,22 @@ SALP_HD void shape_front(const SalpParams& p, const SalpDerived& dv, const Cycle
   st.s.V = V; st.s.I0 = I0n; st.s.I1 = I1n; st.s.com = com; st.s.com_rate = com_rate;
   st.last_update = j;
 }
+template <bool AXI = false>
 SALP_HD void make_coefs(const SalpDerived& dv, const float dir[3], const ShapeFront& f, Coef32& g) {
-  make_coefs(dv, dir, f.jet_on != 0.0f, 0.5f * (dv.init_length_f - f.dl), 0.5f * (dv.init_width_f + f.dl),
+  make_coefs<AXI>(dv, dir, f.jet_on != 0.0f, 0.5f * (dv.init_length_f - f.dl), 0.5f * (dv.init_width_f + f.dl),
              f.I_rate0, f.I_rate1, f.dV_dt, f.com, f.com_rate, f.com_acc, g);
 }
+template <bool AXI>
 SALP_HD void shape_update_at(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c, double t,
                              const float dir[3], int j, int k_T0, int k_jet, ShapeTrack& st, Coef32& g) {
   ShapeFront f;
   shape_front(p, dv, c, t, j, k_T0, k_jet, st, f);
-  make_coefs(dv, dir, f, g);
+  make_coefs<AXI>(dv, dir, f, g);
 }
 
 // ---- building blocks shared by the fused loop below and the pipeline kernel ------------------
 // shape-derived state of the first substep (coefficient set g_0) from the carried columns
+template <bool AXI = false>
 SALP_HD void mixed_init_shape(const SalpParams& p, const SalpDerived& dv, const Body64& b, const float dir[3],
                               ShapeTrack& st, Coef32& g) {
   st.prev_com_rate = b.prev_com_rate;
@@ -509,7 +543,7 @@ SALP_HD void mixed_init_shape(const SalpParams& p, const SalpDerived& dv, const 
   // the carried centre of mass may be stale w.r.t. length/width (Robot.reset quirk, robot.py:478)
   st.s.com = b.com;
   st.s.com_rate = b.com_rate;
-  make_coefs(dv, dir, b.phase == 1, (float)lh, (float)wh,
+  make_coefs<AXI>(dv, dir, b.phase == 1, (float)lh, (float)wh,
              (float)((st.s.I0 - b.prevI[0]) * dv.inv_dt), (float)((st.s.I1 - b.prevI[1]) * dv.inv_dt),
              (float)dV_dt, (float)b.com, (float)b.com_rate, (float)b.com_acc, g);
   st.I0_prev_used = st.s.I0;
@@ -572,7 +606,7 @@ SALP_HD int next_update_after(int j, const PhasePlan& pp) {
          : (j < pp.upd_b_begin ? pp.upd_b_begin : 0x7fffffff);
 }
 
-template <bool NOISE>
+template <bool NOISE, bool AXI>
 SALP_HD int run_cycle_mixed(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c, const double* time_table,
                             Body64& b, double& t_out, RandCtx* rc) {
   // ---- K: first k with !(t_k < total) in the dtype the reference compares in (robot.py:756) ----
@@ -585,7 +619,7 @@ SALP_HD int run_cycle_mixed(const SalpParams& p, const SalpDerived& dv, const Cy
   ShapeTrack st;
   Coef32 g;
   Motion32 s;
-  mixed_init_shape(p, dv, b, dir, st, g);
+  mixed_init_shape<AXI>(p, dv, b, dir, st, g);
   mixed_init_dyn(b, s);
   mixed_init_kin(b, s);
 
@@ -602,8 +636,8 @@ SALP_HD int run_cycle_mixed(const SalpParams& p, const SalpDerived& dv, const Cy
   // lean body.  With the K-sort's second key (end of shape motion) W is close to every lane's own end.
   const int lane_end = pp.upd_a_end > pp.upd_b_end ? pp.upd_a_end : pp.upd_b_end;
   const int W = warp_max_int(lane_end < K ? lane_end : K);
-  dyn_step<NOISE>(dv, g, s, rc, 0);
-  shape_update(p, dv, c, time_table, dir, 1, pp.k_T0, pp.k_jet, st, g);
+  dyn_step<NOISE, false, AXI>(dv, g, s, rc, 0);
+  shape_update<AXI>(p, dv, c, time_table, dir, 1, pp.k_T0, pp.k_jet, st, g);
 
   int k = 1;
   const int kA = W < K ? W : K;                  // part A covers updates j = k + 1 <= W
@@ -617,13 +651,13 @@ SALP_HD int run_cycle_mixed(const SalpParams& p, const SalpDerived& dv, const Cy
     const int aend = kA < cend ? kA : cend;
     for (; k < aend; k++) {
       kin_step(dv, s);
-      dyn_step<NOISE>(dv, g, s, rc, k);
+      dyn_step<NOISE, false, AXI>(dv, g, s, rc, k);
       tj = rn::dadd(tj, p.dt);
-      shape_update_at(p, dv, c, tj, dir, k + 1, pp.k_T0, pp.k_jet, st, g);
+      shape_update_at<AXI>(p, dv, c, tj, dir, k + 1, pp.k_T0, pp.k_jet, st, g);
     }
     for (; k < cend; k++) {
       kin_step(dv, s);
-      dyn_step<NOISE, true>(dv, g, s, rc, k);       // k >= W: the shape is static
+      dyn_step<NOISE, true, AXI>(dv, g, s, rc, k);  // k >= W: the shape is static
     }
     if (k == boundary) flush_chunk(b, s);       // two-level sums (fp32 chunk partials -> fp64 totals)
   }
@@ -645,7 +679,9 @@ template <>
 SALP_HD int run_cycle<SALP_PRECISION_MIXED>(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c,
                                             const double* time_table, Body64& b, double& t_out, RandCtx* rc) {
   (void)rc;
-  return run_cycle_mixed<false>(p, dv, c, time_table, b, t_out, nullptr);
+  // (warp-uniform: dv is a kernel argument; both forms give the same bits for axisymmetric parameters)
+  if (dv.axisym) return run_cycle_mixed<false, true>(p, dv, c, time_table, b, t_out, nullptr);
+  return run_cycle_mixed<false, false>(p, dv, c, time_table, b, t_out, nullptr);
 }
 
 // SalpParams.randomization != 0: per-env coefficient draws (Robot._randomize_parameters,
@@ -683,6 +719,7 @@ SALP_HD int run_cycle<SALP_PRECISION_MIXED_RANDOMIZED>(const SalpParams& p, cons
                                                        RandCtx* rc) {
   SalpDerived k = dv;
   randomize_derived(p, (uint32_t)p.randomization, *rc, k);
-  if (p.randomization & SALP_RAND_DISTURBANCE) return run_cycle_mixed<true>(p, k, c, time_table, b, t_out, rc);
-  return run_cycle_mixed<false>(p, k, c, time_table, b, t_out, rc);
+  // (per-env coefficient draws are not axisymmetric: the general form)
+  if (p.randomization & SALP_RAND_DISTURBANCE) return run_cycle_mixed<true, false>(p, k, c, time_table, b, t_out, rc);
+  return run_cycle_mixed<false, false>(p, k, c, time_table, b, t_out, rc);
 }

@@ -66,32 +66,44 @@ __device__ __forceinline__ void front_load(ShapeFront& f, const float* row) {
   f.dl = a.x; f.I_rate0 = a.y; f.I_rate1 = a.z; f.dV_dt = a.w;
   f.com = b.x; f.com_rate = b.y; f.com_acc = b.z; f.jet_on = b.w;
 }
+// One 112-byte row per lane and slot.  The first five quads are everything the axisymmetric form
+// needs (AXI: two fewer 128-bit accesses per substep on each side); the last two hold the entries
+// that only differ for asymmetric coefficient sets.
+template <bool AXI>
 __device__ __forceinline__ void coef_store(const Coef32& g, float* row) {
   float4* q = reinterpret_cast<float4*>(row);
   q[0] = make_float4(g.aj[0], g.aj[1], g.aj[2], g.kdm[0]);
-  q[1] = make_float4(g.kdm[1], g.kdm[2], g.mrm[0], g.mrm[1]);
-  q[2] = make_float4(g.mrm[2], g.com, g.com_rate2, g.com_acc);
-  q[3] = make_float4(g.tj1, g.tj2, g.kqI[0], g.kqI[1]);
-  q[4] = make_float4(g.kqI[2], g.klI[0], g.klI[1], g.klI[2]);
-  q[5] = make_float4(g.JdI[0], g.JdI[1], g.JdI[2], g.AdI[0]);
-  q[6] = make_float4(g.AdI[1], g.AdI[2], 0.f, 0.f);
+  q[1] = make_float4(g.kdm[1], g.mrm[0], g.com, g.com_rate2);
+  q[2] = make_float4(g.com_acc, g.tj1, g.tj2, g.kqI[0]);
+  q[3] = make_float4(g.kqI[1], g.klI[0], g.klI[1], g.JdI[1]);
+  if (AXI) {
+    q[4] = make_float4(g.AdI[1], 0.f, 0.f, 0.f);
+  } else {
+    q[4] = make_float4(g.AdI[1], g.kdm[2], g.mrm[1], g.mrm[2]);
+    q[5] = make_float4(g.kqI[2], g.klI[2], g.JdI[0], g.JdI[2]);
+    q[6] = make_float4(g.AdI[0], g.AdI[2], 0.f, 0.f);
+  }
 }
+template <bool AXI>
 __device__ __forceinline__ void coef_load(Coef32& g, const float* row) {
   const float4* q = reinterpret_cast<const float4*>(row);
-  float4 a = q[0], b = q[1], c = q[2], d = q[3], e = q[4], f = q[5], h = q[6];
+  float4 a = q[0], b = q[1], c = q[2], d = q[3], e = q[4];
   g.aj[0] = a.x; g.aj[1] = a.y; g.aj[2] = a.z; g.kdm[0] = a.w;
-  g.kdm[1] = b.x; g.kdm[2] = b.y; g.mrm[0] = b.z; g.mrm[1] = b.w;
-  g.mrm[2] = c.x; g.com = c.y; g.com_rate2 = c.z; g.com_acc = c.w;
-  g.tj1 = d.x; g.tj2 = d.y; g.kqI[0] = d.z; g.kqI[1] = d.w;
-  g.kqI[2] = e.x; g.klI[0] = e.y; g.klI[1] = e.z; g.klI[2] = e.w;
-  g.JdI[0] = f.x; g.JdI[1] = f.y; g.JdI[2] = f.z; g.AdI[0] = f.w;
-  g.AdI[1] = h.x; g.AdI[2] = h.y;
+  g.kdm[1] = b.x; g.mrm[0] = b.y; g.com = b.z; g.com_rate2 = b.w;
+  g.com_acc = c.x; g.tj1 = c.y; g.tj2 = c.z; g.kqI[0] = c.w;
+  g.kqI[1] = d.x; g.klI[0] = d.y; g.klI[1] = d.z; g.JdI[1] = d.w;
+  g.AdI[1] = e.x;
+  if (!AXI) {
+    float4 f = q[5], h = q[6];
+    g.kdm[2] = e.y; g.mrm[1] = e.z; g.mrm[2] = e.w;
+    g.kqI[2] = f.x; g.klI[2] = f.y; g.JdI[0] = f.z; g.JdI[2] = f.w;
+    g.AdI[0] = h.x; g.AdI[2] = h.y;
+  }
 }
 
-__global__ void __launch_bounds__(SALP_PIPE_THREADS, 1)
-salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constant__ SalpDerived dv,
-                      const __grid_constant__ SalpView v, const __grid_constant__ SalpStepIO io, uint32_t flags) {
-  extern __shared__ __align__(16) unsigned char pipe_smem[];
+template <bool AXI>
+__device__ __forceinline__ void salp_pipe_body(const SalpParams& p, const SalpDerived& dv, const SalpView& v,
+                                               const SalpStepIO& io, uint32_t flags, unsigned char* pipe_smem) {
   PipeShared& sh = *reinterpret_cast<PipeShared*>(pipe_smem);
   float* tile = reinterpret_cast<float*>(pipe_smem + sizeof(PipeShared));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -129,7 +141,7 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
     ShapeTrack st;
     if (K > 0) {
       Coef32 g0;
-      mixed_init_shape(p, dv, b, dir, st, g0);
+      mixed_init_shape<AXI>(p, dv, b, dir, st, g0);
     }
     double tj = v.time_table[1];                   // carried by the same additions as the table (robot.py:674)
     int j = 1;
@@ -186,21 +198,21 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
           if (j + 1 <= kA) {
             front_load(f0, &sh.ring1[j % SALP_PIPE_SLOTS1][lane][0]);
             front_load(f1, &sh.ring1[(j + 1) % SALP_PIPE_SLOTS1][lane][0]);
-            make_coefs(dv, dir, f0, g0);
-            make_coefs(dv, dir, f1, g1);
-            coef_store(g0, &sh.ring2[j % SALP_PIPE_SLOTS2][lane][0]);
-            coef_store(g1, &sh.ring2[(j + 1) % SALP_PIPE_SLOTS2][lane][0]);
+            make_coefs<AXI>(dv, dir, f0, g0);
+            make_coefs<AXI>(dv, dir, f1, g1);
+            coef_store<AXI>(g0, &sh.ring2[j % SALP_PIPE_SLOTS2][lane][0]);
+            coef_store<AXI>(g1, &sh.ring2[(j + 1) % SALP_PIPE_SLOTS2][lane][0]);
           } else if (j <= kA) {
             front_load(f0, &sh.ring1[j % SALP_PIPE_SLOTS1][lane][0]);
-            make_coefs(dv, dir, f0, g0);
-            coef_store(g0, &sh.ring2[j % SALP_PIPE_SLOTS2][lane][0]);
+            make_coefs<AXI>(dv, dir, f0, g0);
+            coef_store<AXI>(g0, &sh.ring2[j % SALP_PIPE_SLOTS2][lane][0]);
           }
           j += 2;
         } else {
           if (j <= kA) {
             front_load(f0, &sh.ring1[j % SALP_PIPE_SLOTS1][lane][0]);
-            make_coefs(dv, dir, f0, g0);
-            coef_store(g0, &sh.ring2[j % SALP_PIPE_SLOTS2][lane][0]);
+            make_coefs<AXI>(dv, dir, f0, g0);
+            coef_store<AXI>(g0, &sh.ring2[j % SALP_PIPE_SLOTS2][lane][0]);
           }
           j += 1;
         }
@@ -215,10 +227,10 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
     Coef32 g;
     if (K > 0) {
       ShapeTrack st0;
-      mixed_init_shape(p, dv, b, dir, st0, g);      // g_0 (once; cheaper than a hand-off)
+      mixed_init_shape<AXI>(p, dv, b, dir, st0, g);      // g_0 (once; cheaper than a hand-off)
       mixed_init_dyn(b, s);
       mixed_init_kin(b, s);
-      dyn_step(dv, g, s);
+      dyn_step<false, false, AXI>(dv, g, s);
     }
     int kk = 1;
     const int WA = Wmax < Kw - 1 ? Wmax : Kw - 1;   // iterations kk = 1..K-1 exist; those <= W load g_kk
@@ -227,9 +239,9 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
       const int ce = (c + 1) * C < WA ? (c + 1) * C : WA;
       for (; kk <= ce; kk++) {
         if (kk < K) {
-          coef_load(g, &sh.ring2[kk % SALP_PIPE_SLOTS2][lane][0]);
+          coef_load<AXI>(g, &sh.ring2[kk % SALP_PIPE_SLOTS2][lane][0]);
           kin_step(dv, s);
-          dyn_step(dv, g, s);
+          dyn_step<false, false, AXI>(dv, g, s);
           if ((kk & (SALP_MIXED_CHUNK - 1)) == 0) flush_chunk(b, s);
         }
       }
@@ -243,7 +255,7 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
       const int cend = boundary < K ? boundary : K;
       for (; k < cend; k++) {
         kin_step(dv, s);
-        dyn_step<false, true>(dv, g, s);            // k > W: the shape is static
+        dyn_step<false, true, AXI>(dv, g, s);       // k > W: the shape is static
       }
       if (k == boundary) flush_chunk(b, s);
     }
@@ -278,4 +290,13 @@ salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constan
       if (io.terminal_obs) io.terminal_obs[(int64_t)blockIdx.x * 32 * D + j] = tile[32 * D + j];
     }
   }
+}
+
+__global__ void __launch_bounds__(SALP_PIPE_THREADS, 1)
+salp_step_kernel_pipe(const __grid_constant__ SalpParams p, const __grid_constant__ SalpDerived dv,
+                      const __grid_constant__ SalpView v, const __grid_constant__ SalpStepIO io, uint32_t flags) {
+  extern __shared__ __align__(16) unsigned char pipe_smem[];
+  // (block-uniform: dv is a kernel argument; both forms give the same bits for axisymmetric parameters)
+  if (dv.axisym) salp_pipe_body<true>(p, dv, v, io, flags, pipe_smem);
+  else salp_pipe_body<false>(p, dv, v, io, flags, pipe_smem);
 }

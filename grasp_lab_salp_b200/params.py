@@ -23,6 +23,7 @@ STEP_AUTORESET = 1
 STEP_SORT_BY_K = 2
 STEP_PIPELINE = 4
 STEP_FUSED = 8
+STEP_GENERIC = 16
 
 RAND_ACTION, RAND_OBSERVATION, RAND_DYNAMICS, RAND_DISTURBANCE, RAND_LATENCY = 1, 2, 4, 8, 16
 

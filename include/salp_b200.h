@@ -70,6 +70,9 @@ typedef enum SalpPrecision {
  * shape-producer / motion-consumer pipeline kernel; results are bit-identical with the fused one. */
 #define SALP_STEP_PIPELINE 4u      /* force the pipeline kernel (ignored where it does not apply) */
 #define SALP_STEP_FUSED 8u         /* force the fused one-warp kernel */
+/* The loop has a form for axisymmetric coefficient sets (axes 1 and 2 alike, as in the defaults) that
+ * shares their entries; it is chosen automatically and gives the same bits as the general form. */
+#define SALP_STEP_GENERIC 16u      /* force the general form (tests) */
 
 /*
  * Every literal the reference hard-codes on this path, as one POD.

@@ -77,7 +77,8 @@ int salp_reset_host(salp_handle h, const uint8_t* mask, float* obs) {
 int salp_step_host(salp_handle h, const SalpStepIO* io, uint32_t flags) {
   if (!h || !io || !io->actions || !io->obs || !io->reward || !io->terminated || !io->truncated)
     return SALP_ERR_INVALID;
-  const SalpDerived dv = make_derived(h->params);
+  SalpDerived dv = make_derived(h->params);
+  if (flags & SALP_STEP_GENERIC) dv.axisym = 0;
   for (int64_t i = 0; i < h->view.n; i++) {
     if (h->params.precision == SALP_PRECISION_F64)
       env_step<SALP_PRECISION_F64>(h->params, dv, h->view, *io, flags, i);

@@ -101,6 +101,28 @@ def test_redundant_shape_updates_are_exact_noops():
             assert np.array_equal(x, y, equal_nan=True), (t, col)
 
 
+def test_axisymmetric_form_equals_general_form():
+    """The default parameters are axisymmetric (axes 1 and 2 carry the same coefficients); the loop
+    then uses a form that shares their coefficient entries and drops identically-zero terms
+    (SalpDerived.axisym).  Forcing the general form (SALP_STEP_GENERIC) must give the same bits.
+    (Asymmetric parameters take the general form: test_non_default_robot_parameters.)"""
+    from grasp_lab_salp_b200.params import FIELDS
+    g = load_golden("ref_random.npz")
+    n, T = 96, 10
+    acts = np.random.default_rng(5).uniform([0, 0, -1], [1, 1, 1], size=(T, n, 3)).astype(np.float32)
+    a = EmuBatch(n, golden_params(g, precision=PRECISION_MIXED), seed=8)
+    b = EmuBatch(n, golden_params(g, precision=PRECISION_MIXED), seed=8)
+    np.testing.assert_array_equal(a.reset(), b.reset())
+    for t in range(T):
+        ra = a.step(acts[t], auto_reset=True)
+        rb = b.step(acts[t], auto_reset=True, generic=True)
+        for x, y in zip(ra, rb):
+            np.testing.assert_array_equal(x, y)
+        np.testing.assert_array_equal(a.terms, b.terms)
+    for col in FIELDS:
+        np.testing.assert_array_equal(a.get_state(col), b.get_state(col), err_msg=col)
+
+
 @pytest.mark.parametrize("num_obstacles", [0, 1, 5, 8])
 def test_other_obstacle_counts(num_obstacles):
     """Observation width 6 + 2 n, proximity penalty and collision over n obstacles (n = 0: no

@@ -290,6 +290,30 @@ def test_pipeline_kernel_matches_fused_kernel():
     fused.check()
 
 
+@pytest.mark.parametrize("n,pipeline", [(1000, True), (1000, False), (24000, None)])
+def test_axisymmetric_form_equals_general_form(n, pipeline):
+    """SalpDerived.axisym: the form of the loop for axisymmetric coefficient sets (the defaults) vs
+    the general form (SALP_STEP_GENERIC): bit-identical, in the pipeline kernel, the fused kernel
+    and the fused K-sorted kernel."""
+    from grasp_lab_salp_b200.params import FIELDS
+    g = load_golden("ref_random.npz")
+    T = 8 if n <= 4736 else 4
+    acts = uniform_actions(np.random.default_rng(15), T, n)
+    a, b = SalpBatch(n, golden_params(g), seed=6), SalpBatch(n, golden_params(g), seed=6)
+    np.testing.assert_array_equal(a.reset(), b.reset())
+    sort = n > 18944
+    for t in range(T):
+        ra = a.step(acts[t], auto_reset=True, pipeline=pipeline, sort_by_k=sort)
+        rb = b.step(acts[t], auto_reset=True, pipeline=pipeline, sort_by_k=sort, generic=True)
+        for x, y in zip(ra, rb):
+            np.testing.assert_array_equal(x, y)
+        np.testing.assert_array_equal(a.terms, b.terms)
+    for col in FIELDS:
+        np.testing.assert_array_equal(a.get_state(col), b.get_state(col), err_msg=col)
+    a.check()
+    b.check()
+
+
 def test_pipeline_kernel_is_deterministic_at_full_size():
     """Two handles, same seed, same actions, BASELINE's 4096 envs (every SM busy with one
     three-warp block), 40 free-running steps: bit-identical outputs and state.  A missed hand-off

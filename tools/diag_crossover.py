@@ -9,6 +9,7 @@ import torch
 from grasp_lab_salp_b200 import SalpBatch, default_params
 
 PIPE = {None: None, '0': False, '1': True}[os.environ.get('DIAG_PIPELINE')]
+GENERIC = os.environ.get('DIAG_GENERIC') == '1'
 dev = torch.device('cuda', 0)
 import os
 for n in [int(x) for x in os.environ.get('DIAG_NS','18944,24576,32768,42624,49152,65536,98304,131072').split(',')]:
@@ -21,13 +22,13 @@ for n in [int(x) for x in os.environ.get('DIAG_NS','18944,24576,32768,42624,4915
     out = []
     for sort in (False, True):
         for i in range(4):
-            b.step_device(u[i % 8], sort_by_k=sort, pipeline=PIPE)
+            b.step_device(u[i % 8], sort_by_k=sort, pipeline=PIPE, generic=GENERIC)
         steps = 30
         st = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         en = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         for i in range(steps):
             st[i].record()
-            b.step_device(u[i % 8], sort_by_k=sort, pipeline=PIPE)
+            b.step_device(u[i % 8], sort_by_k=sort, pipeline=PIPE, generic=GENERIC)
             en[i].record()
         torch.cuda.synchronize()
         out.append(np.mean([s.elapsed_time(e) for s, e in zip(st, en)]))

@@ -10,6 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from grasp_lab_salp_b200 import SalpBatch, default_params
 
 PIPE = {None: None, '0': False, '1': True}[os.environ.get('DIAG_PIPELINE')]
+GENERIC = os.environ.get('DIAG_GENERIC') == '1'
 dev = torch.device("cuda", 0)
 n = int(os.environ.get("DIAG_N", "4096"))
 b = SalpBatch(n, default_params(), seed=0)
@@ -20,11 +21,11 @@ g.manual_seed(1)
 
 def timed(actions, label, steps=50):
     for _ in range(10):
-        b.step_device(actions, pipeline=PIPE)
+        b.step_device(actions, pipeline=PIPE, generic=GENERIC)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     ev[0].record()
     for i in range(steps):
-        b.step_device(actions, pipeline=PIPE)
+        b.step_device(actions, pipeline=PIPE, generic=GENERIC)
         ev[i + 1].record()
     torch.cuda.synchronize()
     ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))[steps // 2]
