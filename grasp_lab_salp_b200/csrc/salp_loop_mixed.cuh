@@ -340,13 +340,14 @@ SALP_HD void dyn_step(const SalpDerived& dv, const Coef32& g, Motion32& s, RandC
   float sd = fast_norm3(v0, v1, v2) + dv.ratio_f;               // |v| v + ratio v = v (|v| + ratio)
   float w12;                                                    // w1^2 + w2^2
   float wn = fast_norm3(w0, w1, w2, w12);
-  float ev0 = dv.E[0] * v0, ev1 = dv.E[1] * v1, ev2 = dv.E[2] * v2;
-  const float p12 = w1 * w2, p20 = w2 * w0, p01 = w0 * w1;
+  // Every product and sum below is an explicitly rounded operation (fmaf / rn::), so the compiler
+  // has no freedom in how it contracts a*b+c: the general form, the axisymmetric form and the
+  // static-shape form round identically wherever they compute the same quantity, in every kernel.
+  const float ev0 = rn::fmul(dv.E[0], v0), ev1 = rn::fmul(dv.E[1], v1), ev2 = rn::fmul(dv.E[2], v2);
+  const float p12 = rn::fmul(w1, w2), p20 = rn::fmul(w2, w0), p01 = rn::fmul(w0, w1);
+  const float q12 = rn::fmul(v1, v2), q20 = rn::fmul(v2, v0), q01 = rn::fmul(v0, v1);
   // fictitious forces of the moving centre of mass c = (com, 0, 0) (robot.py:806-810):
   //   -(alpha x c) - w x (w x c) - 2 w x c' - c''  with the products of w shared with the Euler equations
-  // (the STATIC form must round exactly like the general one with com_rate2 = com_acc = 0, or results
-  //  would depend on where the warp-uniform loop split falls: explicitly rounded operations, which
-  //  the compiler may not contract with their neighbours)
   const float t1 = rn::fadd(s.al2, p01), t2 = rn::fsub(p20, s.al1);
   float fict0, fict1, fict2;
   if (STATIC) {
@@ -358,21 +359,30 @@ SALP_HD void dyn_step(const SalpDerived& dv, const Coef32& g, Motion32& s, RandC
     fict1 = fmaf(g.com, t1, rn::fmul(w2, g.com_rate2));
     fict2 = fmaf(g.com, t2, -rn::fmul(w1, g.com_rate2));
   }
-  float na0, na1, na2, nl0, nl1, nl2;
-  if (AXI) {     // same values as below with kdm[2] = kdm[1], mrm[i] = mrm[0], JdI[0] = AdI[0] = 0, JdI[2] = -JdI[1], AdI[2] = -AdI[1]
-    na0 = g.aj[0] + v0 * fmaf(g.kdm[0], sd, -g.mrm[0]) - dv.Ca[0] * s.ac0 - (w1 * ev2 - w2 * ev1) + fict0;
-    na1 = g.aj[1] + v1 * fmaf(g.kdm[1], sd, -g.mrm[0]) - dv.Ca[1] * s.ac1 - (w2 * ev0 - w0 * ev2) + fict1;
-    na2 = g.aj[2] + v2 * fmaf(g.kdm[1], sd, -g.mrm[0]) - dv.Ca[2] * s.ac2 - (w0 * ev1 - w1 * ev0) + fict2;
-    nl0 = w0 * fmaf(g.kqI[0], wn, g.klI[0]) - dv.Cat[0] * s.al0;
-    nl1 = g.tj1 + w1 * fmaf(g.kqI[1], wn, g.klI[1]) - dv.Cat[1] * s.al1 - p20 * g.JdI[1] - (v2 * v0) * g.AdI[1];
-    nl2 = g.tj2 + w2 * fmaf(g.kqI[1], wn, g.klI[1]) - dv.Cat[2] * s.al2 + p01 * g.JdI[1] + (v0 * v1) * g.AdI[1];
+  // AXI: kdm[2] = kdm[1], kqI[2] = kqI[1], klI[2] = klI[1], mrm[i] = mrm[0], JdI[0] = AdI[0] = 0,
+  // JdI[2] = -JdI[1], AdI[2] = -AdI[1]
+  const float X0 = fmaf(g.kdm[0], sd, -g.mrm[0]);
+  const float X1 = fmaf(g.kdm[1], sd, AXI ? -g.mrm[0] : -g.mrm[1]);
+  const float X2 = AXI ? X1 : fmaf(g.kdm[2], sd, -g.mrm[2]);
+  const float Y0 = fmaf(g.kqI[0], wn, g.klI[0]);
+  const float Y1 = fmaf(g.kqI[1], wn, g.klI[1]);
+  const float Y2 = AXI ? Y1 : fmaf(g.kqI[2], wn, g.klI[2]);
+  // a_i = aj_i + v_i X_i - Ca_i a_prev,i - (w x (E o v))_i + fict_i
+  float na0 = fmaf(w2, ev1, fmaf(-w1, ev2, fmaf(-dv.Ca[0], s.ac0, fmaf(v0, X0, g.aj[0]))));
+  float na1 = fmaf(w0, ev2, fmaf(-w2, ev0, fmaf(-dv.Ca[1], s.ac1, fmaf(v1, X1, g.aj[1]))));
+  float na2 = fmaf(w1, ev0, fmaf(-w0, ev1, fmaf(-dv.Ca[2], s.ac2, fmaf(v2, X2, g.aj[2]))));
+  na0 = rn::fadd(na0, fict0);
+  na1 = rn::fadd(na1, fict1);
+  na2 = rn::fadd(na2, fict2);
+  // alpha_i = tj_i + w_i Y_i - Cat_i alpha_prev,i - w_i1 w_i2 JdI_i - v_i1 v_i2 AdI_i
+  float nl0 = fmaf(-dv.Cat[0], s.al0, rn::fmul(w0, Y0));
+  float nl1 = fmaf(-q20, g.AdI[1], fmaf(-p20, g.JdI[1], fmaf(-dv.Cat[1], s.al1, fmaf(w1, Y1, g.tj1))));
+  float nl2 = fmaf(-dv.Cat[2], s.al2, fmaf(w2, Y2, g.tj2));
+  if (AXI) {
+    nl2 = fmaf(q01, g.AdI[1], fmaf(p01, g.JdI[1], nl2));
   } else {
-    na0 = g.aj[0] + v0 * fmaf(g.kdm[0], sd, -g.mrm[0]) - dv.Ca[0] * s.ac0 - (w1 * ev2 - w2 * ev1) + fict0;
-    na1 = g.aj[1] + v1 * fmaf(g.kdm[1], sd, -g.mrm[1]) - dv.Ca[1] * s.ac1 - (w2 * ev0 - w0 * ev2) + fict1;
-    na2 = g.aj[2] + v2 * fmaf(g.kdm[2], sd, -g.mrm[2]) - dv.Ca[2] * s.ac2 - (w0 * ev1 - w1 * ev0) + fict2;
-    nl0 = w0 * fmaf(g.kqI[0], wn, g.klI[0]) - dv.Cat[0] * s.al0 - p12 * g.JdI[0] - (v1 * v2) * g.AdI[0];
-    nl1 = g.tj1 + w1 * fmaf(g.kqI[1], wn, g.klI[1]) - dv.Cat[1] * s.al1 - p20 * g.JdI[1] - (v2 * v0) * g.AdI[1];
-    nl2 = g.tj2 + w2 * fmaf(g.kqI[2], wn, g.klI[2]) - dv.Cat[2] * s.al2 - p01 * g.JdI[2] - (v0 * v1) * g.AdI[2];
+    nl0 = fmaf(-q12, g.AdI[0], fmaf(-p12, g.JdI[0], nl0));
+    nl2 = fmaf(-q01, g.AdI[2], fmaf(-p01, g.JdI[2], nl2));
   }
   if (NOISE) {        // force_noise / torque_noise join the sums of _newton_equations / _euler_equations
     ou_step(dv, *rc, k);
