@@ -60,7 +60,7 @@ SALP_HD float fast_norm3(float a, float b, float c) {
 // np_sincosf without the separately-rounded steps: same Cody-Waite + minimax kernels (1 ulp),
 // free to contract.  |x| <= 71476.  Used outside the substep loop (chunk anchors).
 SALP_HD void sincos32(float x, float& sn, float& cs) {
-  float q = (x * 0x1.45f306p-1f + 0x1.8p+23f) - 0x1.8p+23f;
+  float q = rn::fsub(fmaf(x, 0x1.45f306p-1f, 0x1.8p+23f), 0x1.8p+23f);
   float r = fmaf(q, -0x1.921fb0p+0f, x);
   r = fmaf(q, -0x1.5110b4p-22f, r);
   r = fmaf(q, -0x1.846988p-48f, r);
@@ -337,7 +337,7 @@ SALP_HD void ou_step(const SalpDerived& dv, RandCtx& rc, int k) {
 template <bool NOISE = false, bool STATIC = false, bool AXI = false>
 SALP_HD void dyn_step(const SalpDerived& dv, const Coef32& g, Motion32& s, RandCtx* rc = nullptr, int k = 0) {
   const float v0 = s.v0, v1 = s.v1, v2 = s.v2, w0 = s.w0, w1 = s.w1, w2 = s.w2;
-  float sd = fast_norm3(v0, v1, v2) + dv.ratio_f;               // |v| v + ratio v = v (|v| + ratio)
+  const float sd = rn::fadd(fast_norm3(v0, v1, v2), dv.ratio_f);     // |v| v + ratio v = v (|v| + ratio)
   float w12;                                                    // w1^2 + w2^2
   float wn = fast_norm3(w0, w1, w2, w12);
   // Every product and sum below is an explicitly rounded operation (fmaf / rn::), so the compiler
@@ -406,15 +406,16 @@ SALP_HD void dyn_step(const SalpDerived& dv, const Coef32& g, Motion32& s, RandC
 // the increment is clamped (kin_step) so that the pair stays a unit vector; the fp32 increments
 // and the fp64 angle totals accumulate the same clamped values, so the pair and the angle agree
 // and the pair is re-anchored from the total at the next flush.
+// (explicitly rounded operations, like dyn_step: identical bits in every instantiation and kernel)
 SALP_HD void rotate_small(float d, float& sn, float& cs) {
   // per-substep increments are ~1e-2 rad: sin d = d - d^3/6 + d^5/120, cos d = 1 - d^2/2 + d^4/24
   // (truncation < 1e-10 there, 2e-7 at the clamp; dropping the d^5 term was measured to triple the
   //  error of the violent cycles next to the integrator's stability limit)
-  const float d2 = d * d;
-  const float sd_ = d * fmaf(d2, fmaf(d2, 8.3333333e-3f, -1.6666667e-1f), 1.0f);
+  const float d2 = rn::fmul(d, d);
+  const float sd_ = rn::fmul(d, fmaf(d2, fmaf(d2, 8.3333333e-3f, -1.6666667e-1f), 1.0f));
   const float cd_ = fmaf(d2, fmaf(d2, 4.1666667e-2f, -0.5f), 1.0f);
-  float ns = sn * cd_ + cs * sd_;
-  cs = cs * cd_ - sn * sd_;
+  const float ns = fmaf(sn, cd_, rn::fmul(cs, sd_));
+  cs = fmaf(cs, cd_, -rn::fmul(sn, sd_));
   sn = ns;
 }
 SALP_HD float clamp_increment(float d) { return fminf(fmaxf(d, -0.25f), 0.25f); }
@@ -422,23 +423,23 @@ SALP_HD void kin_step(const SalpDerived& dv, Motion32& s) {
   const float dt = dv.dt;
   const float v0 = s.v0, v1 = s.v1, v2 = s.v2, w0 = s.w0, w1 = s.w1, w2 = s.w2;
   const float rcth = fast_rcp(s.cth);          // (not Newton-carried: cos(pitch) changes sign when the body tumbles)
-  float q = s.sph * w1 + s.cph * w2;
+  const float q = fmaf(s.sph, w1, rn::fmul(s.cph, w2));
   // Euler rates (dynamics.py:21-31): psi' = q / cos(theta), phi' = w0 + sin(theta) psi', theta' = cph w1 - sph w2.
   // Only the 1 / cos(theta) terms can ask for more than the Taylor kernels take (see above): the
   // yaw increment is clamped, roll inherits the bound through sin(theta) psi', pitch is clamped too.
-  float dpsi = clamp_increment((q * rcth) * dt);
-  float dphi = fmaf(s.sth, dpsi, w0 * dt);
-  float dtheta = clamp_increment((s.cph * w1 - s.sph * w2) * dt);
-  s.phi_lo += dphi;
-  s.theta_lo += dtheta;
-  s.psi_lo += dpsi;
+  const float dpsi = clamp_increment(rn::fmul(rn::fmul(q, rcth), dt));
+  const float dphi = fmaf(s.sth, dpsi, rn::fmul(w0, dt));
+  const float dtheta = clamp_increment(rn::fmul(fmaf(s.cph, w1, -rn::fmul(s.sph, w2)), dt));
+  s.phi_lo = rn::fadd(s.phi_lo, dphi);
+  s.theta_lo = rn::fadd(s.theta_lo, dtheta);
+  s.psi_lo = rn::fadd(s.psi_lo, dpsi);
   rotate_small(dphi, s.sph, s.cph);
   rotate_small(dtheta, s.sth, s.cth);
   rotate_small(dpsi, s.sps, s.cps);
-  float u1 = s.cph * v1 - s.sph * v2, u2 = s.sph * v1 + s.cph * v2;      // Rx
-  float r0 = s.cth * v0 + s.sth * u2, vw2 = s.cth * u2 - s.sth * v0;     // Ry
-  s.vw0 = s.cps * r0 - s.sps * u1;                                       // Rz
-  s.vw1 = s.sps * r0 + s.cps * u1;
+  const float u1 = fmaf(s.cph, v1, -rn::fmul(s.sph, v2)), u2 = fmaf(s.sph, v1, rn::fmul(s.cph, v2));      // Rx
+  const float r0 = fmaf(s.cth, v0, rn::fmul(s.sth, u2)), vw2 = fmaf(s.cth, u2, -rn::fmul(s.sth, v0));     // Ry
+  s.vw0 = fmaf(s.cps, r0, -rn::fmul(s.sps, u1));                                                          // Rz
+  s.vw1 = fmaf(s.sps, r0, rn::fmul(s.cps, u1));
   s.pw0 = fmaf(s.vw0, dt, s.pw0); s.pw1 = fmaf(s.vw1, dt, s.pw1); s.pw2 = fmaf(vw2, dt, s.pw2);
   s.pos0 = fmaf(v0, dt, s.pos0); s.pos1 = fmaf(v1, dt, s.pos1); s.pos2 = fmaf(v2, dt, s.pos2);
   s.ang0 = fmaf(w0, dt, s.ang0); s.ang1 = fmaf(w1, dt, s.ang1); s.ang2 = fmaf(w2, dt, s.ang2);
