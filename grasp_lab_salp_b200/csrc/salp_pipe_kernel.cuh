@@ -16,9 +16,9 @@
 // Hand-off is chunk-granular (8 substeps; 3 resp. 4 chunks in flight) on named barriers:
 // bar.arrive on the side that is done with a chunk, bar.sync on the side that needs it, so no warp
 // waits unless its neighbour has fallen a whole chunk behind.  The three warps execute the
-// functions of run_cycle_mixed (same fixed 32-substep grouping of the fp32 chunk sums); results
-// agree with the fused kernel to fp32 rounding (the compiler contracts a*b+c differently in the
-// two kernels; tests/test_gpu_parity.py::test_pipeline_kernel_matches_fused_kernel).
+// functions of run_cycle_mixed (same fixed 32-substep grouping of the fp32 chunk sums, every
+// operation of the loop explicitly rounded): results are bit-identical with the fused kernel
+// (tests/test_gpu_parity.py::test_pipeline_kernel_matches_fused_kernel).
 // (Splitting the consumer further into a dyn warp and a kin warp was measured slower, 0.203 vs
 // 0.190 ms per 4096-env step: in one warp the two chains fill each other's latency shadows.)
 #pragma once
