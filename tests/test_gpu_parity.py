@@ -208,7 +208,7 @@ def test_full_size_mixed_vs_f64_trajectory_equivalence():
     f64.check()
 
 
-@pytest.mark.parametrize("n", [512, 12288])      # pipeline kernel (<= 4736 envs per handle) / fused kernel
+@pytest.mark.parametrize("n", [512, 8192, 12288])   # pipeline kernel everywhere / fused whole vs pipeline shards / fused everywhere
 def test_shard_invariance(n):
     """Multi-GPU sharding rule: envs [0,N) on one handle == two handles of N/2 with
     env_id_offset, bit for bit (per-env Philox streams are keyed by the GLOBAL env id; results
