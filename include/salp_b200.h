@@ -66,7 +66,7 @@ typedef enum SalpPrecision {
 /* salp_step flags */
 #define SALP_STEP_AUTORESET 1u     /* SB3 VecEnv semantics: reset finished envs, obs = post-reset obs */
 #define SALP_STEP_SORT_BY_K 2u     /* balance warps: order envs by substep count before the loop */
-/* Kernel choice for small batches (N <= 32 envs per SM, MIXED, natural order).  Default: the 2-warp
+/* Kernel choice for small batches (N <= 32 envs per SM, MIXED, natural order).  Default: the 3-warp
  * shape-producer / motion-consumer pipeline kernel; results are bit-identical with the fused one. */
 #define SALP_STEP_PIPELINE 4u      /* force the pipeline kernel (ignored where it does not apply) */
 #define SALP_STEP_FUSED 8u         /* force the fused one-warp kernel */
