@@ -51,8 +51,14 @@ PROTOTYPES = {
     "salp_trace_cycle": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "salp_check": (C.c_int, [C.c_void_p]),
     "salp_launch_count": (C.c_int64, [C.c_void_p]),
+    "salp_last_step_kernel": (C.c_char_p, [C.c_void_p]),
+    "salp_abi_version": (C.c_int32, []),
+    "salp_sizeof_params": (C.c_int64, []),
+    "salp_sizeof_step_io": (C.c_int64, []),
     "salp_probe_fp32_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
 }
+
+ABI_VERSION = 1        # SALP_ABI_VERSION of include/salp_b200.h this binding mirrors
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsalp_b200.so")
 _cdll = None
@@ -69,17 +75,34 @@ def bind(cdll, names=None):
     return cdll
 
 
+def check_layout(cdll):
+    """A library whose struct layouts differ from the ctypes mirrors would be driven through the
+    wrong offsets: refuse it (stale prebuilt .so, or a header edited without its mirror)."""
+    got = (cdll.salp_abi_version(), cdll.salp_sizeof_params(), cdll.salp_sizeof_step_io())
+    want = (ABI_VERSION, C.sizeof(SalpParams), C.sizeof(SalpStepIO))
+    if got != want:
+        raise ImportError(f"libsalp_b200.so does not match this binding: (abi, sizeof SalpParams, sizeof SalpStepIO) "
+                          f"= {got}, expected {want}; rebuild with `python -m grasp_lab_salp_b200.build --force`")
+
+
 def load():
-    """Load (building in-tree first if the sources are newer and nvcc is available)."""
+    """Load (building in-tree first if the sources changed and nvcc is available)."""
     global _cdll
     if _cdll is not None:
         return _cdll
     from . import build
     try:
         build.build_library()
-    except Exception as e:  # no nvcc on this box: use the prebuilt .so that travelled with the repo
+    except Exception as e:
+        # no nvcc on this box: the prebuilt .so that travelled with the repo is used -- but only if it
+        # was built from exactly these sources (content hash), never a stale one
         if not os.path.exists(LIB_PATH):
             raise ImportError(f"libsalp_b200.so is missing and could not be built ({e}); "
                               "the SALP simulator has no CPU fallback") from e
-    _cdll = bind(C.CDLL(LIB_PATH))
+        if build.is_stale():
+            raise ImportError(f"libsalp_b200.so is stale (sources changed since it was built) and the rebuild "
+                              f"failed: {e}") from e
+    cdll = bind(C.CDLL(LIB_PATH))
+    check_layout(cdll)
+    _cdll = cdll
     return _cdll

@@ -102,6 +102,11 @@ class SalpBatch:
     def launch_count(self) -> int:
         return int(self._L.salp_launch_count(self._h))
 
+    @property
+    def last_step_kernel(self) -> str:
+        """Name of the step kernel the library launched for the last step (salp_last_step_kernel)."""
+        return (self._L.salp_last_step_kernel(self._h) or b"").decode()
+
     # ------------------------------------------------------------------ host (numpy) face
     def set_scene_pool(self, targets, obstacles):
         """Replace the built-in Philox scene sampler by caller-given scenes (parity with an

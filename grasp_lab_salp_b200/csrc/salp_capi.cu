@@ -16,6 +16,7 @@ struct SalpSim {
   int device;
   int obs_dim;
   int64_t launches;
+  const char* last_kernel;
   std::string error;
   // device staging for the *_host entry points
   float* d_actions;
@@ -150,6 +151,10 @@ const char* salp_last_error(salp_handle h) { return h ? h->error.c_str() : g_cre
 int64_t salp_num_envs(salp_handle h) { return h ? h->view.n : 0; }
 int32_t salp_obs_dim(salp_handle h) { return h ? h->obs_dim : 0; }
 int64_t salp_launch_count(salp_handle h) { return h ? h->launches : 0; }
+const char* salp_last_step_kernel(salp_handle h) { return h ? h->last_kernel : ""; }
+int32_t salp_abi_version(void) { return SALP_ABI_VERSION; }
+int64_t salp_sizeof_params(void) { return (int64_t)sizeof(SalpParams); }
+int64_t salp_sizeof_step_io(void) { return (int64_t)sizeof(SalpStepIO); }
 
 int salp_destroy(salp_handle h) {
   if (!h) return SALP_OK;
@@ -204,6 +209,7 @@ int salp_create(const SalpParams* params, int64_t num_envs, int device, uint64_t
   h->device = device;
   h->obs_dim = SALP_OBS_BASE + 2 * params->num_obstacles;
   h->launches = 0;
+  h->last_kernel = "";
   const int64_t n = num_envs;
   const int D = h->obs_dim;
   SalpView& v = h->view;
@@ -276,7 +282,7 @@ int salp_step(salp_handle h, const SalpStepIO* io, uint32_t flags, void* stream)
   if (!io->actions || !io->obs || !io->reward || !io->terminated || !io->truncated)
     return fail(h, SALP_ERR_INVALID, "salp_step: actions, obs, reward, terminated and truncated are required");
   DeviceGuard g(h->device);
-  int rc = salp_launch_step(h->params, h->view, *io, flags, h->scratch, (cudaStream_t)stream);
+  int rc = salp_launch_step(h->params, h->view, *io, flags, h->scratch, (cudaStream_t)stream, &h->last_kernel);
   if (rc < 0) return cuda_fail(h, cudaGetLastError(), "salp_step launch");
   h->launches += rc;
   return SALP_OK;
@@ -321,9 +327,10 @@ static bool zero_copy_enabled() {
 //    overlaps the integration of the other warps and no copy is queued behind the kernel.  The
 //    kernel only ever WRITES those arrays (observation rows are assembled in shared memory).
 //    Actions are read in place for batches of at most one warp per SM sub-partition and staged by
-//    the copy engine above that.  Used for steps in natural env order only.
-//  * staged (pageable caller buffers, K-sorted steps, F64 / pipeline kernels): H2D of the actions, kernel on
-//    the handle's own device buffers, one D2H per output.
+//    the copy engine above that.  Used for steps in natural env order only, whichever MIXED step
+//    kernel the launcher picks (fused or pipeline: all assemble rows in shared memory).
+//  * staged (pageable caller buffers, K-sorted steps, F64): H2D of the actions, kernel on the
+//    handle's own device buffers, one D2H per output.
 // The optional extras (reward_terms, substeps, episode_metrics) are always staged.
 int salp_step_host(salp_handle h, const SalpStepIO* io, uint32_t flags) {
   if (!h || !io) return SALP_ERR_INVALID;
@@ -336,13 +343,13 @@ int salp_step_host(salp_handle h, const SalpStepIO* io, uint32_t flags) {
   // (K-sorted steps visit the envs in scattered order: 40-byte rows make poor PCIe writes --
   //  measured 12.7 ms vs 8.2 ms staged at 1 M envs -- so they keep the staged transport)
   const bool zc_ok = zero_copy_enabled() && h->params.precision == SALP_PRECISION_MIXED &&
-                     !(flags & (SALP_STEP_PIPELINE | SALP_STEP_SORT_BY_K));
+                     !(flags & SALP_STEP_SORT_BY_K);
   float* z_obs = zc_ok ? (float*)mapped_alias(io->obs) : nullptr;
   float* z_reward = zc_ok ? (float*)mapped_alias(io->reward) : nullptr;
   uint8_t* z_term = zc_ok ? (uint8_t*)mapped_alias(io->terminated) : nullptr;
   uint8_t* z_trunc = zc_ok ? (uint8_t*)mapped_alias(io->truncated) : nullptr;
   float* z_tobs = zc_ok ? (float*)mapped_alias(io->terminal_obs) : nullptr;
-  const float* z_act = (zc_ok && n <= (int64_t)148 * 4 * 32)
+  const float* z_act = (zc_ok && n <= (int64_t)h->view.sm_count * 4 * 32)
                            ? (const float*)mapped_alias(io->actions) : nullptr;
   if (!z_act) CU(h, cudaMemcpyAsync(h->d_actions, io->actions, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, s));
   SalpStepIO d;
@@ -355,7 +362,7 @@ int salp_step_host(salp_handle h, const SalpStepIO* io, uint32_t flags) {
   d.reward_terms = io->reward_terms ? h->d_terms : nullptr;
   d.substeps = io->substeps ? h->d_substeps : nullptr;
   d.episode_metrics = io->episode_metrics ? h->d_metrics : nullptr;
-  int rc = salp_launch_step(h->params, h->view, d, flags, h->scratch, s);
+  int rc = salp_launch_step(h->params, h->view, d, flags, h->scratch, s, &h->last_kernel);
   if (rc < 0) return cuda_fail(h, cudaGetLastError(), "salp_step_host launch");
   h->launches += rc;
   if (!z_obs) CU(h, cudaMemcpyAsync(io->obs, d.obs, sizeof(float) * D * n, cudaMemcpyDeviceToHost, s));

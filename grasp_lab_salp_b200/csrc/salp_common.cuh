@@ -58,8 +58,9 @@ struct SalpScratch {
 // Each returns the number of kernels it launched, or a negative SalpStatus.
 int salp_launch_reset(const SalpParams& p, const SalpView& v, const uint8_t* mask, float* obs,
                       cudaStream_t stream);
+// `kernel_name` (nullable) receives the name of the step kernel that was launched.
 int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& io, uint32_t flags,
-                     const SalpScratch& scratch, cudaStream_t stream);
+                     const SalpScratch& scratch, cudaStream_t stream, const char** kernel_name = nullptr);
 int salp_launch_init(const SalpParams& p, const SalpView& v, cudaStream_t stream);
 int salp_launch_trace(const SalpParams& p, const SalpView& v, int64_t env, const float action[3], double* trace,
                       int capacity, int32_t* K_out, cudaStream_t stream);

@@ -5,6 +5,7 @@
 // __grid_constant__: they sit in the constant bank and every access is a uniform c[][] operand.
 #include "salp_step_kernel.cuh"
 #include "salp_pipe_kernel.cuh"
+#include "salp_pipe4_kernel.cuh"
 
 __global__ void salp_init_kernel(const __grid_constant__ SalpParams p, const __grid_constant__ SalpView v) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -109,8 +110,10 @@ int salp_launch_trace(const SalpParams& p, const SalpView& v, int64_t env, const
 }
 
 int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& io, uint32_t flags,
-                     const SalpScratch& scratch, cudaStream_t stream) {
+                     const SalpScratch& scratch, cudaStream_t stream, const char** kernel_name) {
   int launches = 0;
+  const char* dummy;
+  const char*& name = kernel_name ? *kernel_name : dummy;
   const int32_t* order = nullptr;
   SalpDerived dv = make_derived(p);
   if (flags & SALP_STEP_GENERIC) dv.axisym = 0;      // the general form of the loop even for axisymmetric coefficient sets
@@ -125,10 +128,14 @@ int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& i
     order = scratch.order;
   }
   const int block = block_for(v.n);
-  // batches that fit one three-warp block per SM: the producer / consumer pipeline
-  // (salp_pipe_kernel.cuh), unless SALP_STEP_FUSED asks for the one-warp kernel
-  if (p.precision == SALP_PRECISION_MIXED && p.randomization == 0 && !order && !(flags & SALP_STEP_FUSED) &&
-      v.n <= (int64_t)32 * (v.sm_count > 0 ? v.sm_count : 148)) {
+  // Small batches: the warp-specialised pipeline kernels, unless SALP_STEP_FUSED asks for the
+  // one-warp kernel.  Default: the four-warp kernel (salp_pipe4_kernel.cuh) for up to two blocks
+  // (64 envs) per SM, natural or K-sorted order.  SALP_PIPE_VARIANT=3 selects the round-1
+  // three-warp kernel (one block per SM, natural order) for A/B measurements.
+  const int sms = v.sm_count > 0 ? v.sm_count : 148;
+  static const int variant = [] { const char* e = getenv("SALP_PIPE_VARIANT"); return e ? atoi(e) : 4; }();
+  const bool pipe_ok = p.precision == SALP_PRECISION_MIXED && p.randomization == 0 && !(flags & SALP_STEP_FUSED);
+  if (pipe_ok && variant == 3 && !order && v.n <= (int64_t)32 * sms) {
     static bool configured[64] = {};              // per device: the opt-in is a per-device function attribute
     int dev = 0;
     cudaGetDevice(&dev);
@@ -141,17 +148,41 @@ int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& i
       if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     salp_step_kernel_pipe<<<grid_for(v.n, 32), SALP_PIPE_THREADS, pipe_smem_bytes(p), stream>>>(p, dv, v, io, flags);
+    name = "salp_step_kernel_pipe";
     SALP_LAUNCH_CHECK();
     return launches + 1;
   }
-  if (p.precision == SALP_PRECISION_F64)
+  if (pipe_ok && variant != 3 && v.n <= (int64_t)64 * sms) {
+    static bool configured4[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured4[dev]) {
+      SalpParams widest = p;
+      widest.num_obstacles = SALP_MAX_OBSTACLES;
+      if (cudaFuncSetAttribute(salp_step_kernel_pipe4, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)pipe4_smem_bytes(widest, false)) != cudaSuccess)
+        return SALP_ERR_CUDA;
+      if (dev >= 0 && dev < 64) configured4[dev] = true;
+    }
+    salp_step_kernel_pipe4<<<grid_for(v.n, 32), SALP_P4_THREADS, pipe4_smem_bytes(p, dv.axisym != 0), stream>>>(
+        p, dv, v, io, flags, order);
+    name = "salp_step_kernel_pipe4";
+    SALP_LAUNCH_CHECK();
+    return launches + 1;
+  }
+  if (p.precision == SALP_PRECISION_F64) {
     salp_launch_step_f64(p, v, io, flags, order, stream);     // salp_step_f64.cu (compiled with -fmad=false)
-  else if (p.randomization != 0)       // default-off robustness switches: separate instantiation
+    name = "salp_step_kernel<F64>";
+  } else if (p.randomization != 0) {   // default-off robustness switches: separate instantiation
     salp_step_kernel_lat<SALP_PRECISION_MIXED_RANDOMIZED><<<grid_for(v.n, 32), 32, lat_tile_bytes(p), stream>>>(p, dv, v, io, flags, order);
-  else if (block == 32)
+    name = "salp_step_kernel_lat<MIXED_RANDOMIZED>";
+  } else if (block == 32) {
     salp_step_kernel_lat<SALP_PRECISION_MIXED><<<grid_for(v.n, 32), 32, lat_tile_bytes(p), stream>>>(p, dv, v, io, flags, order);
-  else
+    name = "salp_step_kernel_lat<MIXED>";
+  } else {
     salp_step_kernel<SALP_PRECISION_MIXED><<<grid_for(v.n, block), block, 0, stream>>>(p, dv, v, io, flags, order);
+    name = "salp_step_kernel<MIXED>";
+  }
   SALP_LAUNCH_CHECK();
   return launches + 1;
 }

@@ -27,7 +27,8 @@
 
 #define SALP_MIXED_CHUNK 32
 
-// ---- MUFU-based reciprocal / norm with one Newton step (~1 ulp, no slow-path branches) --------
+// ---- MUFU-based reciprocal / square root ----------------------------------------------------
+// fast_rcp: MUFU.RCP + one Newton step (~1 ulp), for the coefficient set (make_coefs).
 SALP_HD float fast_rcp(float x) {
 #ifdef __CUDA_ARCH__
   float r;
@@ -37,16 +38,26 @@ SALP_HD float fast_rcp(float x) {
   return 1.0f / x;
 #endif
 }
-// bc2 = b^2 + c^2, the partial sum on the way (the fictitious force needs w1^2 + w2^2)
-SALP_HD float fast_norm3(float a, float b, float c, float& bc2) {
-  bc2 = fmaf(b, b, c * c);
-  float s = fmaf(a, a, bc2);
+// Inside the substep loop: the bare MUFU results (rcp.approx / sqrt.approx: max relative error
+// 2^-23 resp. ~1 ulp per the PTX ISA, i.e. at the level of one fp32 rounding) -- one instruction
+// on the v -> |v| -> a -> v recurrence instead of seed + Newton step (6 dependent instructions).
+SALP_HD float loop_rcp(float x) {
 #ifdef __CUDA_ARCH__
   float r;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(s, 1e-35f)));
-  float y = s * r;
-  float e = fmaf(-y, y, s);
-  return fmaf(0.5f * r, e, y);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / x;
+#endif
+}
+// bc2 = b^2 + c^2, the partial sum on the way (the fictitious force needs w1^2 + w2^2)
+SALP_HD float fast_norm3(float a, float b, float c, float& bc2) {
+  bc2 = fmaf(b, b, rn::fmul(c, c));
+  const float s = fmaf(a, a, bc2);
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
+  return r;
 #else
   return sqrtf(s);
 #endif
@@ -162,7 +173,7 @@ SALP_HD SalpDerived make_derived(const SalpParams& p) {
 // fp32 coefficient set of one substep: everything the Newton/Euler equations need from the body
 // shape, pre-divided by mass / inertia.  Loop-invariant while the shape is static.  With
 //   M = m, Ca/Car/Cat the added-mass diagonals, E = 1 + Ca, J_i = I_i (1 + Cat_i):
-//   a_i     = aj_i + v_i (kdm_i (|v| + ratio) - mrm_i) - Ca_i a_prev,i - (w x (E o v))_i + fict_i
+//   a_i     = aj_i + v_i (kdm_i |v| + xc_i) - Ca_i a_prev,i - (w x (E o v))_i + fict_i,  xc_i = kdm_i ratio - mrm_i
 //   alpha_i = tj_i + w_i (kqI_i |w| + klI_i) - Cat_i alpha_prev,i - w_i1 w_i2 JdI_i - v_i1 v_i2 AdI_i
 // which is robot.py:789-851 / dynamics.py:6-174 with the common factors 1/m, 1/I_i cancelled
 // (Coriolis and added-mass cross products merged; the two cross products of a vector with its own
@@ -170,7 +181,7 @@ SALP_HD SalpDerived make_derived(const SalpParams& p) {
 struct Coef32 {
   float aj[3];        // F_jet / m                                       (robot.py:937-951)
   float kdm[3];       // -rho/2 area_i Ct_i / m                          (dynamics.py:111-116)
-  float mrm[3];       // mass_rate Car_i / m                             (dynamics.py:139)
+  float xc[3];        // kdm_i ratio - mass_rate Car_i / m                (dynamics.py:111-116, :139)
   float com, com_rate2, com_acc;      // centre of mass, 2 x its rate, its acceleration     robot.py:898-922
   float tj1, tj2;     // (arm x F_jet)_i / I_i                           (robot.py:931-935)
   float kqI[3];       // -rho/2 Cr_i area_i dims_i / I_i                 (dynamics.py:120-128)
@@ -232,7 +243,7 @@ SALP_HD void shape64_step(const SalpParams& p, const SalpDerived& k, double lh, 
 // All fp32 coefficients of the coming substep.  Mass, inertia, areas and drag coefficients are
 // evaluated in fp32 from the half-length / half-width (they are never differenced); the
 // differenced quantities arrive from the fp64 chain already rounded.
-// AXI (SalpDerived.axisym): entries [2] of kdm / kqI / klI equal entries [1], mrm[1] = mrm[2] = mrm[0],
+// AXI (SalpDerived.axisym): entries [2] of kdm / xc / kqI / klI equal entries [1],
 // JdI[0] = AdI[0] = 0, JdI[2] = -JdI[1], AdI[2] = -AdI[1] -- they are neither computed nor read.
 template <bool AXI = false>
 SALP_HD void make_coefs(const SalpDerived& k, const float dir[3], bool jet_on, float lh, float wh,
@@ -257,10 +268,14 @@ SALP_HD void make_coefs(const SalpDerived& k, const float dir[3], bool jet_on, f
   const float ct0 = fmaf(-nr, k.tspan[0], k.thi[0]), ct1 = fmaf(-nr, k.tspan[1], k.thi[1]);
   const float cr0 = fmaf(-nr, k.rspan[0], k.rhi[0]), cr1 = fmaf(-nr, k.rspan[1], k.rhi[1]);
   g.kdm[0] = Q0 * ct0; g.kdm[1] = Q1 * ct1;
-  if (!AXI) g.kdm[2] = Q1 * fmaf(-nr, k.tspan[2], k.thi[2]);
   const float mr = (k.rho_f * dV_dt) * inv_m;                      // mass_rate / m   (geometry.py:98-101)
-  g.mrm[0] = mr * k.Car[0];
-  if (!AXI) { g.mrm[1] = mr * k.Car[1]; g.mrm[2] = mr * k.Car[2]; }
+  // v_i (kdm_i (|v| + ratio) - mr Car_i) = v_i (kdm_i |v| + xc_i)
+  g.xc[0] = fmaf(g.kdm[0], k.ratio_f, -(mr * k.Car[0]));
+  g.xc[1] = fmaf(g.kdm[1], k.ratio_f, -(mr * k.Car[1]));
+  if (!AXI) {
+    g.kdm[2] = Q1 * fmaf(-nr, k.tspan[2], k.thi[2]);
+    g.xc[2] = fmaf(g.kdm[2], k.ratio_f, -(mr * k.Car[2]));
+  }
   const float f = jet_on ? k.jet_gain_f * dV_dt * dV_dt : 0.0f;
   const float fm = f * inv_m;
   g.aj[0] = dir[0] * fm; g.aj[1] = dir[1] * fm; g.aj[2] = dir[2] * fm;
@@ -337,59 +352,61 @@ SALP_HD void ou_step(const SalpDerived& dv, RandCtx& rc, int k) {
 template <bool NOISE = false, bool STATIC = false, bool AXI = false>
 SALP_HD void dyn_step(const SalpDerived& dv, const Coef32& g, Motion32& s, RandCtx* rc = nullptr, int k = 0) {
   const float v0 = s.v0, v1 = s.v1, v2 = s.v2, w0 = s.w0, w1 = s.w1, w2 = s.w2;
-  const float sd = rn::fadd(fast_norm3(v0, v1, v2), dv.ratio_f);     // |v| v + ratio v = v (|v| + ratio)
+  // The recurrence v -> |v| -> a -> v is the critical path of the whole kernel when the GPU is not
+  // full: |v| and |w| are one MUFU.SQRT each, and they enter LAST -- everything that does not depend
+  // on them (added mass, Coriolis, fictitious forces, the jet) is summed first, in the shadow of
+  // the square roots:   a_i = base_i + v_i X_i,  X_i = kdm_i |v| + xc_i      (|v| v + ratio v = v (|v| + ratio))
+  const float nv = fast_norm3(v0, v1, v2);
   float w12;                                                    // w1^2 + w2^2
-  float wn = fast_norm3(w0, w1, w2, w12);
+  const float wn = fast_norm3(w0, w1, w2, w12);
   // Every product and sum below is an explicitly rounded operation (fmaf / rn::), so the compiler
   // has no freedom in how it contracts a*b+c: the general form, the axisymmetric form and the
   // static-shape form round identically wherever they compute the same quantity, in every kernel.
   const float ev0 = rn::fmul(dv.E[0], v0), ev1 = rn::fmul(dv.E[1], v1), ev2 = rn::fmul(dv.E[2], v2);
-  const float p12 = rn::fmul(w1, w2), p20 = rn::fmul(w2, w0), p01 = rn::fmul(w0, w1);
-  const float q12 = rn::fmul(v1, v2), q20 = rn::fmul(v2, v0), q01 = rn::fmul(v0, v1);
+  const float p20 = rn::fmul(w2, w0), p01 = rn::fmul(w0, w1);
+  const float q20 = rn::fmul(v2, v0), q01 = rn::fmul(v0, v1);
+  // a_i - v_i X_i = aj_i - Ca_i a_prev,i - (w x (E o v))_i + fict_i
+  float ba0 = fmaf(w2, ev1, fmaf(-w1, ev2, fmaf(-dv.Ca[0], s.ac0, g.aj[0])));
+  float ba1 = fmaf(w0, ev2, fmaf(-w2, ev0, fmaf(-dv.Ca[1], s.ac1, g.aj[1])));
+  float ba2 = fmaf(w1, ev0, fmaf(-w0, ev1, fmaf(-dv.Ca[2], s.ac2, g.aj[2])));
   // fictitious forces of the moving centre of mass c = (com, 0, 0) (robot.py:806-810):
   //   -(alpha x c) - w x (w x c) - 2 w x c' - c''  with the products of w shared with the Euler equations
   const float t1 = rn::fadd(s.al2, p01), t2 = rn::fsub(p20, s.al1);
-  float fict0, fict1, fict2;
-  if (STATIC) {
-    fict0 = rn::fmul(-g.com, w12);
-    fict1 = rn::fmul(g.com, t1);
-    fict2 = rn::fmul(g.com, t2);
-  } else {
-    fict0 = fmaf(-g.com, w12, g.com_acc);
-    fict1 = fmaf(g.com, t1, rn::fmul(w2, g.com_rate2));
-    fict2 = fmaf(g.com, t2, -rn::fmul(w1, g.com_rate2));
+  if (!STATIC) {      // (com_rate = com_acc = 0 exactly while the shape is static: these three are then exact no-ops)
+    ba0 = rn::fadd(ba0, g.com_acc);
+    ba1 = fmaf(w2, g.com_rate2, ba1);
+    ba2 = fmaf(-w1, g.com_rate2, ba2);
   }
-  // AXI: kdm[2] = kdm[1], kqI[2] = kqI[1], klI[2] = klI[1], mrm[i] = mrm[0], JdI[0] = AdI[0] = 0,
+  ba0 = fmaf(-g.com, w12, ba0);
+  ba1 = fmaf(g.com, t1, ba1);
+  ba2 = fmaf(g.com, t2, ba2);
+  // alpha_i - w_i Y_i = tj_i - Cat_i alpha_prev,i - w_i1 w_i2 JdI_i - v_i1 v_i2 AdI_i
+  // AXI: kdm[2] = kdm[1], xc[2] = xc[1], kqI[2] = kqI[1], klI[2] = klI[1], JdI[0] = AdI[0] = 0,
   // JdI[2] = -JdI[1], AdI[2] = -AdI[1]
-  const float X0 = fmaf(g.kdm[0], sd, -g.mrm[0]);
-  const float X1 = fmaf(g.kdm[1], sd, AXI ? -g.mrm[0] : -g.mrm[1]);
-  const float X2 = AXI ? X1 : fmaf(g.kdm[2], sd, -g.mrm[2]);
-  const float Y0 = fmaf(g.kqI[0], wn, g.klI[0]);
-  const float Y1 = fmaf(g.kqI[1], wn, g.klI[1]);
-  const float Y2 = AXI ? Y1 : fmaf(g.kqI[2], wn, g.klI[2]);
-  // a_i = aj_i + v_i X_i - Ca_i a_prev,i - (w x (E o v))_i + fict_i
-  float na0 = fmaf(w2, ev1, fmaf(-w1, ev2, fmaf(-dv.Ca[0], s.ac0, fmaf(v0, X0, g.aj[0]))));
-  float na1 = fmaf(w0, ev2, fmaf(-w2, ev0, fmaf(-dv.Ca[1], s.ac1, fmaf(v1, X1, g.aj[1]))));
-  float na2 = fmaf(w1, ev0, fmaf(-w0, ev1, fmaf(-dv.Ca[2], s.ac2, fmaf(v2, X2, g.aj[2]))));
-  na0 = rn::fadd(na0, fict0);
-  na1 = rn::fadd(na1, fict1);
-  na2 = rn::fadd(na2, fict2);
-  // alpha_i = tj_i + w_i Y_i - Cat_i alpha_prev,i - w_i1 w_i2 JdI_i - v_i1 v_i2 AdI_i
-  float nl0 = fmaf(-dv.Cat[0], s.al0, rn::fmul(w0, Y0));
-  float nl1 = fmaf(-q20, g.AdI[1], fmaf(-p20, g.JdI[1], fmaf(-dv.Cat[1], s.al1, fmaf(w1, Y1, g.tj1))));
-  float nl2 = fmaf(-dv.Cat[2], s.al2, fmaf(w2, Y2, g.tj2));
+  float bl0 = rn::fmul(-dv.Cat[0], s.al0);
+  float bl1 = fmaf(-q20, g.AdI[1], fmaf(-p20, g.JdI[1], fmaf(-dv.Cat[1], s.al1, g.tj1)));
+  float bl2 = fmaf(-dv.Cat[2], s.al2, g.tj2);
   if (AXI) {
-    nl2 = fmaf(q01, g.AdI[1], fmaf(p01, g.JdI[1], nl2));
+    bl2 = fmaf(q01, g.AdI[1], fmaf(p01, g.JdI[1], bl2));
   } else {
-    nl0 = fmaf(-q12, g.AdI[0], fmaf(-p12, g.JdI[0], nl0));
-    nl2 = fmaf(-q01, g.AdI[2], fmaf(-p01, g.JdI[2], nl2));
+    const float p12 = rn::fmul(w1, w2), q12 = rn::fmul(v1, v2);
+    bl0 = fmaf(-q12, g.AdI[0], fmaf(-p12, g.JdI[0], bl0));
+    bl2 = fmaf(-q01, g.AdI[2], fmaf(-p01, g.JdI[2], bl2));
   }
   if (NOISE) {        // force_noise / torque_noise join the sums of _newton_equations / _euler_equations
     ou_step(dv, *rc, k);
-    na0 = fmaf(rc->ou_fx, g.inv_m, na0);
-    na1 = fmaf(rc->ou_fy, g.inv_m, na1);
-    nl2 = fmaf(rc->ou_tz, g.inv_Iz, nl2);
+    ba0 = fmaf(rc->ou_fx, g.inv_m, ba0);
+    ba1 = fmaf(rc->ou_fy, g.inv_m, ba1);
+    bl2 = fmaf(rc->ou_tz, g.inv_Iz, bl2);
   }
+  const float X0 = fmaf(g.kdm[0], nv, g.xc[0]);
+  const float X1 = fmaf(g.kdm[1], nv, g.xc[1]);
+  const float X2 = AXI ? X1 : fmaf(g.kdm[2], nv, g.xc[2]);
+  const float Y0 = fmaf(g.kqI[0], wn, g.klI[0]);
+  const float Y1 = fmaf(g.kqI[1], wn, g.klI[1]);
+  const float Y2 = AXI ? Y1 : fmaf(g.kqI[2], wn, g.klI[2]);
+  const float na0 = fmaf(v0, X0, ba0), na1 = fmaf(v1, X1, ba1), na2 = fmaf(v2, X2, ba2);
+  const float nl0 = fmaf(w0, Y0, bl0), nl1 = fmaf(w1, Y1, bl1), nl2 = fmaf(w2, Y2, bl2);
   s.ac0 = na0; s.ac1 = na1; s.ac2 = na2;
   s.al0 = nl0; s.al1 = nl1; s.al2 = nl2;
   s.v0 = fmaf(na0, dv.dt, v0); s.v1 = fmaf(na1, dv.dt, v1); s.v2 = fmaf(na2, dv.dt, v2);
@@ -419,10 +436,13 @@ SALP_HD void rotate_small(float d, float& sn, float& cs) {
   sn = ns;
 }
 SALP_HD float clamp_increment(float d) { return fminf(fmaxf(d, -0.25f), 0.25f); }
-SALP_HD void kin_step(const SalpDerived& dv, Motion32& s) {
+// kin_step = kin_world (Euler angles, world position) + kin_body (the body-frame integrals
+// `position`, `angle` of robot.py:872-875).  The two halves share no state, so the four-warp
+// pipeline kernel runs them on different warps (kin_body rides with the dynamics, which owns v, w).
+SALP_HD void kin_world(const SalpDerived& dv, Motion32& s) {
   const float dt = dv.dt;
   const float v0 = s.v0, v1 = s.v1, v2 = s.v2, w0 = s.w0, w1 = s.w1, w2 = s.w2;
-  const float rcth = fast_rcp(s.cth);          // (not Newton-carried: cos(pitch) changes sign when the body tumbles)
+  const float rcth = loop_rcp(s.cth);          // (a pure function of cos(pitch): nothing carried, it changes sign when the body tumbles)
   const float q = fmaf(s.sph, w1, rn::fmul(s.cph, w2));
   // Euler rates (dynamics.py:21-31): psi' = q / cos(theta), phi' = w0 + sin(theta) psi', theta' = cph w1 - sph w2.
   // Only the 1 / cos(theta) terms can ask for more than the Taylor kernels take (see above): the
@@ -441,8 +461,15 @@ SALP_HD void kin_step(const SalpDerived& dv, Motion32& s) {
   s.vw0 = fmaf(s.cps, r0, -rn::fmul(s.sps, u1));                                                          // Rz
   s.vw1 = fmaf(s.sps, r0, rn::fmul(s.cps, u1));
   s.pw0 = fmaf(s.vw0, dt, s.pw0); s.pw1 = fmaf(s.vw1, dt, s.pw1); s.pw2 = fmaf(vw2, dt, s.pw2);
-  s.pos0 = fmaf(v0, dt, s.pos0); s.pos1 = fmaf(v1, dt, s.pos1); s.pos2 = fmaf(v2, dt, s.pos2);
-  s.ang0 = fmaf(w0, dt, s.ang0); s.ang1 = fmaf(w1, dt, s.ang1); s.ang2 = fmaf(w2, dt, s.ang2);
+}
+SALP_HD void kin_body(const SalpDerived& dv, Motion32& s) {
+  const float dt = dv.dt;
+  s.pos0 = fmaf(s.v0, dt, s.pos0); s.pos1 = fmaf(s.v1, dt, s.pos1); s.pos2 = fmaf(s.v2, dt, s.pos2);
+  s.ang0 = fmaf(s.w0, dt, s.ang0); s.ang1 = fmaf(s.w1, dt, s.ang1); s.ang2 = fmaf(s.w2, dt, s.ang2);
+}
+SALP_HD void kin_step(const SalpDerived& dv, Motion32& s) {
+  kin_world(dv, s);
+  kin_body(dv, s);
 }
 
 // (sin, cos) of an fp64 angle total, rounded to fp32: the chunk anchor.  The fp64 argument is split
@@ -458,18 +485,25 @@ SALP_HD void anchor_sincos(double x, float& sn, float& cs) {
 }
 
 // fold the fp32 chunk partials into the fp64 totals and re-anchor the three (sin, cos) pairs
-SALP_HD void flush_chunk(Body64& b, Motion32& s) {
+// (flush_world / flush_body: the halves that belong to kin_world / kin_body)
+SALP_HD void flush_world(Body64& b, Motion32& s) {
   b.pw[0] += (double)s.pw0; b.pw[1] += (double)s.pw1; b.pw[2] += (double)s.pw2;
-  b.pos[0] += (double)s.pos0; b.pos[1] += (double)s.pos1; b.pos[2] += (double)s.pos2;
-  b.ang[0] += (double)s.ang0; b.ang[1] += (double)s.ang1; b.ang[2] += (double)s.ang2;
   b.eul[0] += (double)s.phi_lo; b.eul[1] += (double)s.theta_lo; b.eul[2] += (double)s.psi_lo;
   anchor_sincos(b.eul[0], s.sph, s.cph);
   anchor_sincos(b.eul[1], s.sth, s.cth);
   anchor_sincos(b.eul[2], s.sps, s.cps);
   s.phi_lo = s.theta_lo = s.psi_lo = 0.f;
   s.pw0 = s.pw1 = s.pw2 = 0.f;
+}
+SALP_HD void flush_body(Body64& b, Motion32& s) {
+  b.pos[0] += (double)s.pos0; b.pos[1] += (double)s.pos1; b.pos[2] += (double)s.pos2;
+  b.ang[0] += (double)s.ang0; b.ang[1] += (double)s.ang1; b.ang[2] += (double)s.ang2;
   s.pos0 = s.pos1 = s.pos2 = 0.f;
   s.ang0 = s.ang1 = s.ang2 = 0.f;
+}
+SALP_HD void flush_chunk(Body64& b, Motion32& s) {
+  flush_world(b, s);
+  flush_body(b, s);
 }
 
 // Shape bookkeeping in fp64 (everything the reference differences) + the fp32 coefficient set.

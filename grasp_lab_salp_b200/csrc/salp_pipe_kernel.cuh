@@ -73,13 +73,13 @@ template <bool AXI>
 __device__ __forceinline__ void coef_store(const Coef32& g, float* row) {
   float4* q = reinterpret_cast<float4*>(row);
   q[0] = make_float4(g.aj[0], g.aj[1], g.aj[2], g.kdm[0]);
-  q[1] = make_float4(g.kdm[1], g.mrm[0], g.com, g.com_rate2);
+  q[1] = make_float4(g.kdm[1], g.xc[0], g.com, g.com_rate2);
   q[2] = make_float4(g.com_acc, g.tj1, g.tj2, g.kqI[0]);
   q[3] = make_float4(g.kqI[1], g.klI[0], g.klI[1], g.JdI[1]);
   if (AXI) {
-    q[4] = make_float4(g.AdI[1], 0.f, 0.f, 0.f);
+    q[4] = make_float4(g.AdI[1], g.xc[1], 0.f, 0.f);
   } else {
-    q[4] = make_float4(g.AdI[1], g.kdm[2], g.mrm[1], g.mrm[2]);
+    q[4] = make_float4(g.AdI[1], g.xc[1], g.kdm[2], g.xc[2]);
     q[5] = make_float4(g.kqI[2], g.klI[2], g.JdI[0], g.JdI[2]);
     q[6] = make_float4(g.AdI[0], g.AdI[2], 0.f, 0.f);
   }
@@ -89,13 +89,13 @@ __device__ __forceinline__ void coef_load(Coef32& g, const float* row) {
   const float4* q = reinterpret_cast<const float4*>(row);
   float4 a = q[0], b = q[1], c = q[2], d = q[3], e = q[4];
   g.aj[0] = a.x; g.aj[1] = a.y; g.aj[2] = a.z; g.kdm[0] = a.w;
-  g.kdm[1] = b.x; g.mrm[0] = b.y; g.com = b.z; g.com_rate2 = b.w;
+  g.kdm[1] = b.x; g.xc[0] = b.y; g.com = b.z; g.com_rate2 = b.w;
   g.com_acc = c.x; g.tj1 = c.y; g.tj2 = c.z; g.kqI[0] = c.w;
   g.kqI[1] = d.x; g.klI[0] = d.y; g.klI[1] = d.z; g.JdI[1] = d.w;
-  g.AdI[1] = e.x;
+  g.AdI[1] = e.x; g.xc[1] = e.y;
   if (!AXI) {
     float4 f = q[5], h = q[6];
-    g.kdm[2] = e.y; g.mrm[1] = e.z; g.mrm[2] = e.w;
+    g.kdm[2] = e.z; g.xc[2] = e.w;
     g.kqI[2] = f.x; g.klI[2] = f.y; g.JdI[0] = f.z; g.JdI[2] = f.w;
     g.AdI[0] = h.x; g.AdI[2] = h.y;
   }

@@ -66,9 +66,10 @@ typedef enum SalpPrecision {
 /* salp_step flags */
 #define SALP_STEP_AUTORESET 1u     /* SB3 VecEnv semantics: reset finished envs, obs = post-reset obs */
 #define SALP_STEP_SORT_BY_K 2u     /* balance warps: order envs by substep count before the loop */
-/* Kernel choice for small batches (N <= 32 envs per SM, MIXED, natural order).  Default: the 3-warp
- * shape-producer / motion-consumer pipeline kernel; results are bit-identical with the fused one. */
-#define SALP_STEP_PIPELINE 4u      /* force the pipeline kernel (ignored where it does not apply) */
+/* Kernel choice for small batches (N <= 64 envs per SM, MIXED).  Default there: the warp-specialised
+ * pipeline kernel (shape / coefficient / dynamics / kinematics warps); results are bit-identical
+ * with the fused one-warp kernel. */
+#define SALP_STEP_PIPELINE 4u      /* accepted for compatibility: the pipeline kernel is the default where it applies */
 #define SALP_STEP_FUSED 8u         /* force the fused one-warp kernel */
 /* The loop has a form for axisymmetric coefficient sets (axes 1 and 2 alike, as in the defaults) that
  * shares their entries; it is chosen automatically and gives the same bits as the general form. */
@@ -275,6 +276,15 @@ int salp_check(salp_handle h);
 
 /* Kernel launches issued by this handle so far (bench.py reports it as gpu_launches). */
 int64_t salp_launch_count(salp_handle h);
+/* Name of the step kernel the last salp_step / salp_step_host call launched (the launcher picks by
+ * batch size, precision and flags); static string, "" before the first step. */
+const char* salp_last_step_kernel(salp_handle h);
+
+/* Layout checks for bindings that mirror the structs (ctypes): a host whose mirror disagrees with
+ * these must refuse to drive the library. */
+int32_t salp_abi_version(void);
+int64_t salp_sizeof_params(void);
+int64_t salp_sizeof_step_io(void);
 
 /* Measurement tooling (no reference counterpart): register-resident FFMA micro-benchmark on
  * `device`; writes the sustained FP32 rate in TFLOP/s (2 flop per FMA) over ~`millis` ms.

@@ -44,7 +44,24 @@ METRIC_COLS = {"path_length": 2, "direct_distance": 3, "path_efficiency": 4, "fi
 
 
 def load_golden(name):
-    return np.load(os.path.join(GOLDEN_DIR, name), allow_pickle=False)
+    """Golden trace as a dict-like.  The long-horizon sets (tools/gen_golden_long.py) store the
+    post-reset observations and the episode metrics sparsely (one row per ended episode) and have
+    no per-component reward terms; they are densified here to the layout replay_golden reads."""
+    g = np.load(os.path.join(GOLDEN_DIR, name), allow_pickle=False)
+    if "reset_env" not in g.files:
+        return g
+    g = {k: g[k] for k in g.files}
+    e, t = g.pop("reset_env"), g.pop("reset_t")
+    reset_obs = g["obs"].copy()
+    reset_obs[e, t] = g.pop("reset_obs_rows")
+    g["reset_obs"] = reset_obs
+    rows = g.pop("metrics_rows")
+    if len(rows) == len(e):
+        n, T = g["K"].shape
+        metrics = np.full((n, T, rows.shape[1]), np.nan)
+        metrics[e, t] = rows
+        g["metrics"] = metrics
+    return g
 
 
 def golden_params(g, **kw):
@@ -79,12 +96,19 @@ TOL_MIXED = dict(rtol=1e-5, floor=0.1, small_floor=0.1, accel_rtol=1e-4, accel_f
 
 def replay_golden(backend, g, rtol, *, small_rtol=None, small_floor=1e-7, floor=1e-9, accel_rtol=None,
                   accel_floor=1e-6, reward_floor=1e-3, obs_floor=1e-4, metric_floor=1e-6,
-                  check_metrics=True, report=None):
+                  check_metrics=True, report=None, regular_tilt=None):
     """Drive `backend` with the golden actions/scenes and compare every recorded quantity.
 
     Integer/flag quantities (K, cycle, phase, terminated, truncated, hence reset indices)
     must be bit-exact; floats within `rtol` relative (absolute floor `floor`; `small_floor`
     for the near-zero out-of-plane channels).  Returns the worst relative error seen.
+
+    regular_tilt: the model's out-of-plane motion is unstable -- |roll|, |pitch| grow about an
+    e-fold per 25 cycles in the reference -- and once they reach O(1) rad the Euler-rate matrix
+    (dynamics.py:21-31) passes its pitch = +-pi/2 singularity and the trajectory is chaotic: the
+    reference does not reproduce ITSELF there under a 1e-15 perturbation.  With
+    regular_tilt set, floats of an env are compared only while the GOLDEN max(|roll|, |pitch|) of
+    its current episode has stayed below that angle; integers and flags are compared always.
     """
     actions = g["actions"]
     n, T, _ = actions.shape
@@ -94,6 +118,8 @@ def replay_golden(backend, g, rtol, *, small_rtol=None, small_floor=1e-7, floor=
     obs0 = backend.reset()
     np.testing.assert_allclose(obs0, g["first_obs"], rtol=max(rtol, 1e-6), atol=1e-6)
     worst = {}
+    regular = np.ones(n, bool)
+    compared = chaotic_flag_mismatch = 0
 
     def track(key, err):
         worst[key] = max(worst.get(key, 0.0), float(np.max(err)) if np.size(err) else 0.0)
@@ -101,17 +127,32 @@ def replay_golden(backend, g, rtol, *, small_rtol=None, small_floor=1e-7, floor=
     for t in range(T):
         obs, rew, term, trunc = backend.step(actions[:, t], auto_reset=False)
         ctx = f"step {t}"
+        if regular_tilt is not None:
+            tilt = np.maximum(np.abs(g["state"][:, t, names.index("euler_x")]),
+                              np.abs(g["state"][:, t, names.index("euler_y")]))
+            regular &= tilt < regular_tilt
+        compared += int(regular.sum())
         np.testing.assert_array_equal(backend.substeps, g["K"][:, t], err_msg=f"K {ctx}")
         np.testing.assert_array_equal(backend.get_state("cycle"), g["cycle"][:, t], err_msg=f"cycle {ctx}")
         np.testing.assert_array_equal(backend.get_state("phase"), g["phase"][:, t], err_msg=f"phase {ctx}")
-        np.testing.assert_array_equal(term.astype(np.uint8), g["terminated"][:, t], err_msg=f"terminated {ctx}")
-        np.testing.assert_array_equal(trunc.astype(np.uint8), g["truncated"][:, t], err_msg=f"truncated {ctx}")
+        g_term, g_trunc = g["terminated"][:, t].astype(bool), g["truncated"][:, t].astype(bool)
+        # (in the chaotic regime the position is not reproducible, so neither are the position-dependent
+        #  flags; the cycle-count truncation of salp_robot_env.py:274-276 is, and is checked everywhere)
+        np.testing.assert_array_equal(term.astype(bool)[regular], g_term[regular], err_msg=f"terminated {ctx}")
+        np.testing.assert_array_equal(trunc.astype(bool)[regular], g_trunc[regular], err_msg=f"truncated {ctx}")
+        timed_out = g["cycle"][:, t] >= backend.params.max_cycles
+        assert trunc.astype(bool)[timed_out].all(), f"cycle >= max_cycles must truncate, {ctx}"
+        chaotic_flag_mismatch += int(((term.astype(bool) != g_term) | (trunc.astype(bool) != g_trunc))[~regular].sum())
         for j, nm in enumerate(names):
             col = STATE_MAP.get(nm)
-            if col is None:
+            if col is None and nm != "volume":
                 continue
             ref = g["state"][:, t, j]
-            got = backend.get_state(col)
+            if nm == "volume":      # Robot.volume (robot.py:1055-1056) is not carried: ellipsoid(length, width) - tube
+                lh, wh = 0.5 * backend.get_state("length"), 0.5 * backend.get_state("width")
+                got = (4.0 / 3.0) * np.pi * lh * wh * wh - backend.params.tube_volume
+            else:
+                got = backend.get_state(col)
             fl = small_floor if nm in SMALL_CHANNELS else floor
             if nm in ANGLE_CHANNELS and floor >= 0.1:
                 fl = max(fl, 1.0)
@@ -123,28 +164,30 @@ def replay_golden(backend, g, rtol, *, small_rtol=None, small_floor=1e-7, floor=
                 tol = max(tol, accel_rtol or 0.0)
             finite = np.isfinite(ref)
             np.testing.assert_array_equal(np.isfinite(got), finite, err_msg=f"{nm} finiteness {ctx}")
+            finite = finite & regular
             e = rel_err(got[finite], ref[finite], fl)
             track(nm, e)
             assert np.all(e <= tol), f"{nm} {ctx}: rel err {e.max():.3e} > {tol:g} (got {got}, ref {ref})"
-        fin = np.isfinite(g["reward"][:, t])
+        fin = np.isfinite(g["reward"][:, t]) & regular
         e = rel_err(rew[fin], g["reward"][:, t][fin], reward_floor)
         track("reward", e)
         assert np.all(e <= max(rtol, 1e-6) * 10), f"reward {ctx}: {e.max():.3e}"
-        tf = np.isfinite(g["terms"][:, t])
-        e = rel_err(backend.terms[:, :7][tf], g["terms"][:, t][tf], reward_floor)
-        track("reward_terms", e)
-        assert np.all(e <= max(rtol, 1e-6) * 10), f"reward terms {ctx}: {e.max():.3e}"
-        of = np.isfinite(g["obs"][:, t])
+        if "terms" in g:
+            tf = np.isfinite(g["terms"][:, t]) & regular[:, None]
+            e = rel_err(backend.terms[:, :7][tf], g["terms"][:, t][tf], reward_floor)
+            track("reward_terms", e)
+            assert np.all(e <= max(rtol, 1e-6) * 10), f"reward terms {ctx}: {e.max():.3e}"
+        of = np.isfinite(g["obs"][:, t]) & regular[:, None]
         e = rel_err(obs[of], g["obs"][:, t][of], obs_floor)
         track("obs", e)
         assert np.all(e <= max(rtol, 2e-7) * 10), f"obs {ctx}: {e.max():.3e}"
-        ended = (term.astype(bool) | trunc.astype(bool))
-        if check_metrics and ended.any():
+        ended = g_term | g_trunc          # resets follow the golden episode structure (== the backend's wherever flags are compared)
+        if check_metrics and "metrics" in g and ended.any():
             keys = [str(k) for k in g["metric_keys"]]
             for j, k in enumerate(keys):
                 ref = g["metrics"][ended, t, j]
                 got = backend.metrics[ended, METRIC_COLS[k]]
-                ok = np.isfinite(ref)
+                ok = np.isfinite(ref) & regular[ended]
                 e = rel_err(got[ok], ref[ok], metric_floor)
                 track("metrics", e)
                 assert np.all(e <= max(rtol, 1e-6) * 10), f"metric {k} {ctx}: {e.max():.3e}"
@@ -152,9 +195,12 @@ def replay_golden(backend, g, rtol, *, small_rtol=None, small_floor=1e-7, floor=
             obs_r = backend.reset(mask=ended.astype(np.uint8))
             np.testing.assert_allclose(obs_r[ended], g["reset_obs"][ended, t], rtol=1e-6, atol=1e-7,
                                        err_msg=f"post-reset obs {ctx}")
+            regular[ended] = True
+    worst["float_rows_compared"] = compared
+    worst["chaotic_flag_mismatches"] = chaotic_flag_mismatch
     if report is not None:
         report.update(worst)
-    return max(worst.values()) if worst else 0.0
+    return max(v for k, v in worst.items() if k not in ("float_rows_compared", "chaotic_flag_mismatches"))
 
 
 # ---------------------------------------------------------------------------------------------
