@@ -4,7 +4,6 @@
 // of an env in registers.  Kernel arguments (SalpParams, SalpView, SalpStepIO) are
 // __grid_constant__: they sit in the constant bank and every access is a uniform c[][] operand.
 #include "salp_step_kernel.cuh"
-#include "salp_pipe_kernel.cuh"
 #include "salp_pipe4_kernel.cuh"
 
 __global__ void salp_init_kernel(const __grid_constant__ SalpParams p, const __grid_constant__ SalpView v) {
@@ -128,31 +127,13 @@ int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& i
     order = scratch.order;
   }
   const int block = block_for(v.n);
-  // Small batches: the warp-specialised pipeline kernels, unless SALP_STEP_FUSED asks for the
-  // one-warp kernel.  Default: the four-warp kernel (salp_pipe4_kernel.cuh) for up to two blocks
-  // (64 envs) per SM, natural or K-sorted order.  SALP_PIPE_VARIANT=3 selects the round-1
-  // three-warp kernel (one block per SM, natural order) for A/B measurements.
+  // Small batches (at most one 32-env block per SM): the warp-specialised pipeline kernel
+  // (salp_pipe4_kernel.cuh), natural or K-sorted order, unless SALP_STEP_FUSED asks for the one-warp
+  // kernel.  (Two co-resident blocks share the sub-partitions and were measured slower than the
+  // fused kernel: 222 vs 192 us at 9472 envs.)
   const int sms = v.sm_count > 0 ? v.sm_count : 148;
-  static const int variant = [] { const char* e = getenv("SALP_PIPE_VARIANT"); return e ? atoi(e) : 4; }();
   const bool pipe_ok = p.precision == SALP_PRECISION_MIXED && p.randomization == 0 && !(flags & SALP_STEP_FUSED);
-  if (pipe_ok && variant == 3 && !order && v.n <= (int64_t)32 * sms) {
-    static bool configured[64] = {};              // per device: the opt-in is a per-device function attribute
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !configured[dev]) {
-      SalpParams widest = p;
-      widest.num_obstacles = SALP_MAX_OBSTACLES;
-      if (cudaFuncSetAttribute(salp_step_kernel_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)pipe_smem_bytes(widest)) != cudaSuccess)
-        return SALP_ERR_CUDA;
-      if (dev >= 0 && dev < 64) configured[dev] = true;
-    }
-    salp_step_kernel_pipe<<<grid_for(v.n, 32), SALP_PIPE_THREADS, pipe_smem_bytes(p), stream>>>(p, dv, v, io, flags);
-    name = "salp_step_kernel_pipe";
-    SALP_LAUNCH_CHECK();
-    return launches + 1;
-  }
-  if (pipe_ok && variant != 3 && v.n <= (int64_t)64 * sms) {
+  if (pipe_ok && v.n <= (int64_t)32 * sms) {
     static bool configured4[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);

@@ -28,19 +28,9 @@
 #define SALP_MIXED_CHUNK 32
 
 // ---- MUFU-based reciprocal / square root ----------------------------------------------------
-// fast_rcp: MUFU.RCP + one Newton step (~1 ulp), for the coefficient set (make_coefs).
-SALP_HD float fast_rcp(float x) {
-#ifdef __CUDA_ARCH__
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return fmaf(r, fmaf(-x, r, 1.0f), r);
-#else
-  return 1.0f / x;
-#endif
-}
-// Inside the substep loop: the bare MUFU results (rcp.approx / sqrt.approx: max relative error
-// 2^-23 resp. ~1 ulp per the PTX ISA, i.e. at the level of one fp32 rounding) -- one instruction
-// on the v -> |v| -> a -> v recurrence instead of seed + Newton step (6 dependent instructions).
+// The bare MUFU results (rcp.approx / sqrt.approx: max relative error 2^-23 resp. ~1 ulp per the
+// PTX ISA, i.e. at the level of one fp32 rounding) -- one instruction on the v -> |v| -> a -> v
+// recurrence and in the coefficient set instead of seed + Newton step (6 dependent instructions).
 SALP_HD float loop_rcp(float x) {
 #ifdef __CUDA_ARCH__
   float r;
@@ -245,71 +235,98 @@ SALP_HD void shape64_step(const SalpParams& p, const SalpDerived& k, double lh, 
 // differenced quantities arrive from the fp64 chain already rounded.
 // AXI (SalpDerived.axisym): entries [2] of kdm / xc / kqI / klI equal entries [1],
 // JdI[0] = AdI[0] = 0, JdI[2] = -JdI[1], AdI[2] = -AdI[1] -- they are neither computed nor read.
+//
+// The set comes in two halves that the five-warp pipeline kernel computes on different warps:
+//   make_coefs_T  translational: jet acceleration, drag / mass-rate terms, centre-of-mass terms
+//   make_coefs_R  rotational:    jet torque, rotational drag, deformation, inertia ratios
+// Both start from the same handful of shape quantities (CoefBase, ~20 instructions, computed by
+// each half).  EVERY operation is explicitly rounded (rn:: / fmaf), so the halves give the same
+// bits wherever they are inlined -- the fused kernel's make_coefs is just base + T + R.
+struct CoefBase {
+  float wh2, lh2, lw, m, sw, nr, P0, P1, f;
+};
+SALP_HD void coef_base(const SalpDerived& k, bool jet_on, float lh, float wh, float dV_dt, CoefBase& c) {
+  c.wh2 = rn::fmul(wh, wh);
+  c.lh2 = rn::fmul(lh, lh);
+  c.lw = rn::fmul(lh, wh);
+  const float Ve = rn::fmul(k.four_thirds_pi_f, rn::fmul(c.lw, wh));   // geometry.py:79-81
+  c.m = fmaf(k.rho_f, Ve, k.m_base_f);                                 // robot.py:1055-1063
+  c.sw = fmaf(200.0f, Ve, k.skin3_f);                                  // geometry.py:134-183
+  // aspect-ratio interpolation of the drag coefficients (geometry.py:105-123)
+  const float nr = rn::fmul(fmaf(lh, loop_rcp(wh), -k.end_aspect), k.inv_aspect_span);
+  c.nr = fminf(fmaxf(nr, 0.0f), 1.0f);
+  // -rho/2 * area_i (geometry.py:68-75: areas pi wh^2, pi lh wh, pi lh wh)
+  c.P0 = rn::fmul(k.half_rho_pi, c.wh2);
+  c.P1 = rn::fmul(k.half_rho_pi, c.lw);
+  c.f = jet_on ? rn::fmul(rn::fmul(k.jet_gain_f, dV_dt), dV_dt) : 0.0f;   // F_jet = -Cd rho (dV/dt)^2 / A_nozzle
+}
+template <bool AXI = false>
+SALP_HD void make_coefs_T(const SalpDerived& k, const CoefBase& c, const float dir[3], float dV_dt, float com,
+                          float com_rate, float com_acc, Coef32& g) {
+  const float inv_m = loop_rcp(c.m);
+  const float Q0 = rn::fmul(c.P0, inv_m), Q1 = rn::fmul(c.P1, inv_m);
+  g.kdm[0] = rn::fmul(Q0, fmaf(-c.nr, k.tspan[0], k.thi[0]));
+  g.kdm[1] = rn::fmul(Q1, fmaf(-c.nr, k.tspan[1], k.thi[1]));
+  const float mr = rn::fmul(rn::fmul(k.rho_f, dV_dt), inv_m);         // mass_rate / m   (geometry.py:98-101)
+  // v_i (kdm_i (|v| + ratio) - mr Car_i) = v_i (kdm_i |v| + xc_i)
+  g.xc[0] = fmaf(g.kdm[0], k.ratio_f, -rn::fmul(mr, k.Car[0]));
+  g.xc[1] = fmaf(g.kdm[1], k.ratio_f, -rn::fmul(mr, k.Car[1]));
+  if (!AXI) {
+    g.kdm[2] = rn::fmul(Q1, fmaf(-c.nr, k.tspan[2], k.thi[2]));
+    g.xc[2] = fmaf(g.kdm[2], k.ratio_f, -rn::fmul(mr, k.Car[2]));
+  }
+  const float fm = rn::fmul(c.f, inv_m);
+  g.aj[0] = rn::fmul(dir[0], fm); g.aj[1] = rn::fmul(dir[1], fm); g.aj[2] = rn::fmul(dir[2], fm);
+  g.com = com;
+  g.com_rate2 = rn::fadd(com_rate, com_rate);
+  g.com_acc = com_acc;
+  g.inv_m = inv_m;
+}
+template <bool AXI = false>
+SALP_HD void make_coefs_R(const SalpDerived& k, const CoefBase& c, const float dir[3], float lh, float wh,
+                          float I_rate0, float I_rate1, Coef32& g) {
+  const float swh = rn::fmul(c.sw, c.wh2);
+  const float I0 = rn::fadd(swh, swh);
+  const float I1 = fmaf(c.sw, rn::fadd(c.lh2, c.wh2), fmaf(k.c2_f, c.lh2, fmaf(k.c1_f, lh, k.c0_f)));
+  const float inv_I0 = loop_rcp(I0), inv_I1 = loop_rcp(I1);
+  const float kr0 = rn::fmul(c.P0, fmaf(-c.nr, k.rspan[0], k.rhi[0]));
+  const float kr1 = rn::fmul(c.P1, fmaf(-c.nr, k.rspan[1], k.rhi[1]));
+  // drag torque: dims = (width^3, length^3, length^3) = 8 (wh^3, lh^3, lh^3)
+  const float E0 = rn::fmul(rn::fmul(c.wh2, wh), rn::fmul(8.0f, inv_I0));
+  const float E1 = rn::fmul(rn::fmul(c.lh2, lh), rn::fmul(8.0f, inv_I1));
+  g.kqI[0] = rn::fmul(kr0, E0); g.kqI[1] = rn::fmul(kr1, E1);
+  const float tw = rn::fmul(k.torque_ratio, rn::fadd(wh, wh));
+  g.klI[0] = rn::fmul(fmaf(kr0, tw, -I_rate0), inv_I0);
+  g.klI[1] = rn::fmul(fmaf(kr1, tw, -I_rate1), inv_I1);
+  if (!AXI) {
+    const float kr2 = rn::fmul(c.P1, fmaf(-c.nr, k.rspan[2], k.rhi[2]));
+    g.kqI[2] = rn::fmul(kr2, E1);
+    g.klI[2] = rn::fmul(fmaf(kr2, tw, -I_rate1), inv_I1);
+  }
+  // (J_i2 - J_i1) / I_i with J = I o (1 + Cat), I = (I0, I1, I1)
+  const float r01 = rn::fmul(I0, inv_I1);
+  g.JdI[1] = fmaf(r01, k.CatF[0], -k.CatF[2]);
+  const float mI1 = rn::fmul(c.m, inv_I1);
+  g.AdI[1] = rn::fmul(mI1, k.CaD[1]);
+  if (!AXI) {
+    g.JdI[0] = rn::fmul(rn::fmul(I1, inv_I0), rn::fsub(k.CatF[2], k.CatF[1]));
+    g.JdI[2] = fmaf(-r01, k.CatF[0], k.CatF[1]);
+    g.AdI[0] = rn::fmul(rn::fmul(c.m, inv_I0), k.CaD[0]);
+    g.AdI[2] = rn::fmul(mI1, k.CaD[2]);
+  }
+  const float afI = rn::fmul(rn::fsub(k.arm0, lh), rn::fmul(c.f, inv_I1));   // arm = (arm0 - lh, 0, 0)   robot.py:931-935
+  g.tj1 = rn::fmul(-afI, dir[2]);
+  g.tj2 = rn::fmul(afI, dir[1]);
+  g.inv_Iz = inv_I1;
+}
 template <bool AXI = false>
 SALP_HD void make_coefs(const SalpDerived& k, const float dir[3], bool jet_on, float lh, float wh,
                         float I_rate0, float I_rate1, float dV_dt, float com, float com_rate, float com_acc,
                         Coef32& g) {
-  // common sub-products are shared by hand (the compiler may not reassociate): ~85 instructions
-  const float wh2 = wh * wh, lh2 = lh * lh, lw = lh * wh;
-  const float Ve = k.four_thirds_pi_f * (lw * wh);                 // geometry.py:79-81
-  const float m = fmaf(k.rho_f, Ve, k.m_base_f);                   // robot.py:1055-1063
-  const float sw = fmaf(200.0f, Ve, k.skin3_f);                    // geometry.py:134-183
-  const float swh = sw * wh2;
-  const float I0 = swh + swh;
-  const float I1 = fmaf(sw, lh2 + wh2, fmaf(k.c2_f, lh2, fmaf(k.c1_f, lh, k.c0_f)));
-  const float inv_m = fast_rcp(m);
-  const float inv_I0 = fast_rcp(I0), inv_I1 = fast_rcp(I1);
-  // aspect-ratio interpolation of the drag coefficients (geometry.py:105-123)
-  float nr = (lh * fast_rcp(wh) - k.end_aspect) * k.inv_aspect_span;
-  nr = fminf(fmaxf(nr, 0.0f), 1.0f);
-  // -rho/2 * area_i (geometry.py:68-75: areas pi wh^2, pi lh wh, pi lh wh)
-  const float P0 = k.half_rho_pi * wh2, P1 = k.half_rho_pi * lw;
-  const float Q0 = P0 * inv_m, Q1 = P1 * inv_m;
-  const float ct0 = fmaf(-nr, k.tspan[0], k.thi[0]), ct1 = fmaf(-nr, k.tspan[1], k.thi[1]);
-  const float cr0 = fmaf(-nr, k.rspan[0], k.rhi[0]), cr1 = fmaf(-nr, k.rspan[1], k.rhi[1]);
-  g.kdm[0] = Q0 * ct0; g.kdm[1] = Q1 * ct1;
-  const float mr = (k.rho_f * dV_dt) * inv_m;                      // mass_rate / m   (geometry.py:98-101)
-  // v_i (kdm_i (|v| + ratio) - mr Car_i) = v_i (kdm_i |v| + xc_i)
-  g.xc[0] = fmaf(g.kdm[0], k.ratio_f, -(mr * k.Car[0]));
-  g.xc[1] = fmaf(g.kdm[1], k.ratio_f, -(mr * k.Car[1]));
-  if (!AXI) {
-    g.kdm[2] = Q1 * fmaf(-nr, k.tspan[2], k.thi[2]);
-    g.xc[2] = fmaf(g.kdm[2], k.ratio_f, -(mr * k.Car[2]));
-  }
-  const float f = jet_on ? k.jet_gain_f * dV_dt * dV_dt : 0.0f;
-  const float fm = f * inv_m;
-  g.aj[0] = dir[0] * fm; g.aj[1] = dir[1] * fm; g.aj[2] = dir[2] * fm;
-  const float kr0 = P0 * cr0, kr1 = P1 * cr1;
-  // drag torque: dims = (width^3, length^3, length^3) = 8 (wh^3, lh^3, lh^3)
-  const float E0 = (wh2 * wh) * (8.0f * inv_I0), E1 = (lh2 * lh) * (8.0f * inv_I1);
-  g.kqI[0] = kr0 * E0; g.kqI[1] = kr1 * E1;
-  const float tw = k.torque_ratio * (wh + wh);
-  g.klI[0] = fmaf(kr0, tw, -I_rate0) * inv_I0;
-  g.klI[1] = fmaf(kr1, tw, -I_rate1) * inv_I1;
-  if (!AXI) {
-    const float kr2 = P1 * fmaf(-nr, k.rspan[2], k.rhi[2]);
-    g.kqI[2] = kr2 * E1;
-    g.klI[2] = fmaf(kr2, tw, -I_rate1) * inv_I1;
-  }
-  // (J_i2 - J_i1) / I_i with J = I o (1 + Cat), I = (I0, I1, I1)
-  const float r01 = I0 * inv_I1;
-  g.JdI[1] = fmaf(r01, k.CatF[0], -k.CatF[2]);
-  const float mI1 = m * inv_I1;
-  g.AdI[1] = mI1 * k.CaD[1];
-  if (!AXI) {
-    g.JdI[0] = (I1 * inv_I0) * (k.CatF[2] - k.CatF[1]);
-    g.JdI[2] = fmaf(-r01, k.CatF[0], k.CatF[1]);
-    g.AdI[0] = (m * inv_I0) * k.CaD[0];
-    g.AdI[2] = mI1 * k.CaD[2];
-  }
-  g.inv_m = inv_m;
-  g.inv_Iz = inv_I1;
-  const float afI = (k.arm0 - lh) * (f * inv_I1);                  // arm = (arm0 - lh, 0, 0)   robot.py:931-935
-  g.tj1 = -afI * dir[2];
-  g.tj2 = afI * dir[1];
-  g.com = com;
-  g.com_rate2 = com_rate + com_rate;
-  g.com_acc = com_acc;
+  CoefBase c;
+  coef_base(k, jet_on, lh, wh, dV_dt, c);
+  make_coefs_T<AXI>(k, c, dir, dV_dt, com, com_rate, com_acc, g);
+  make_coefs_R<AXI>(k, c, dir, lh, wh, I_rate0, I_rate1, g);
 }
 
 // fp32 register state of one env inside the substep loop
@@ -559,10 +576,26 @@ SALP_HD void shape_front(const SalpParams& p, const SalpDerived& dv, const Cycle
   st.s.V = V; st.s.I0 = I0n; st.s.I1 = I1n; st.s.com = com; st.s.com_rate = com_rate;
   st.last_update = j;
 }
+SALP_HD float front_lh(const SalpDerived& dv, const ShapeFront& f) { return rn::fmul(0.5f, rn::fsub(dv.init_length_f, f.dl)); }
+SALP_HD float front_wh(const SalpDerived& dv, const ShapeFront& f) { return rn::fmul(0.5f, rn::fadd(dv.init_width_f, f.dl)); }
 template <bool AXI = false>
 SALP_HD void make_coefs(const SalpDerived& dv, const float dir[3], const ShapeFront& f, Coef32& g) {
-  make_coefs<AXI>(dv, dir, f.jet_on != 0.0f, 0.5f * (dv.init_length_f - f.dl), 0.5f * (dv.init_width_f + f.dl),
+  make_coefs<AXI>(dv, dir, f.jet_on != 0.0f, front_lh(dv, f), front_wh(dv, f),
              f.I_rate0, f.I_rate1, f.dV_dt, f.com, f.com_rate, f.com_acc, g);
+}
+// the two halves from a ShapeFront (five-warp pipeline kernel)
+template <bool AXI = false>
+SALP_HD void make_coefs_T(const SalpDerived& dv, const float dir[3], const ShapeFront& f, Coef32& g) {
+  CoefBase c;
+  coef_base(dv, f.jet_on != 0.0f, front_lh(dv, f), front_wh(dv, f), f.dV_dt, c);
+  make_coefs_T<AXI>(dv, c, dir, f.dV_dt, f.com, f.com_rate, f.com_acc, g);
+}
+template <bool AXI = false>
+SALP_HD void make_coefs_R(const SalpDerived& dv, const float dir[3], const ShapeFront& f, Coef32& g) {
+  CoefBase c;
+  const float lh = front_lh(dv, f), wh = front_wh(dv, f);
+  coef_base(dv, f.jet_on != 0.0f, lh, wh, f.dV_dt, c);
+  make_coefs_R<AXI>(dv, c, dir, lh, wh, f.I_rate0, f.I_rate1, g);
 }
 template <bool AXI>
 SALP_HD void shape_update_at(const SalpParams& p, const SalpDerived& dv, const CyclePlan& c, double t,

@@ -1,34 +1,38 @@
-// salp_pipe4_kernel.cuh -- the small-batch step kernel, four warps per 32 envs.
+// salp_pipe4_kernel.cuh -- the small-batch step kernel: four warps per 32 envs.
 //
 // With a few thousand envs the GPU is almost empty and one env-step costs K_max (~1340 substeps of
-// the slowest env) x the time ONE warp needs per substep; that warp is bound by instruction issue
-// (ncu: the three-warp kernel's consumer issues on ~80 % of its scheduler's cycles).  So the
-// substep is cut along its feed-forward structure into four instruction streams, one warp each,
-// each warp on its own SM sub-partition:
+// the slowest env) x the time ONE warp needs per substep -- and a lone warp issues well below one
+// instruction per cycle on this code (measured: 150-160 cycles for the 129 instructions of a coast
+// substep, ~400 while the shape moves).  So the substep is cut along its feed-forward structure
+// (salp_pipe_kernel.cuh) into four instruction streams, one warp each, each warp on its own SM
+// sub-partition:
 //
-//   warp 3 (front) : fp64 shape chain + backward differences of substep j      -> ring 1  (8 floats / lane)
-//   warp 2 (coefs) : the stateless fp32 coefficient set from ring 1            -> ring 2  (20 or 28 floats)
-//   warp 0 (dyn)   : the ONLY recurrence that feeds back: (v, w, a, alpha) of substep j from ring 2,
-//                    plus the body-frame integrals (kin_body: they only need v, w)  -> ring 3  (v, w: 6 floats)
-//   warp 1 (kin)   : Euler angles and world position from the (v, w) stream (kin_world); nothing
+//   warp 3 (front)   fp64 shape chain + backward differences of substep j               -> ring 1
+//   warp 2 (coefs R) rotational half of the fp32 coefficient set from ring 1           -> ring 2
+//   warp 0 (dyn)     the ONLY recurrence that feeds back: (v, w, a, alpha) of substep j.  It computes
+//                    the translational half of the coefficient set itself, from ring 1 -- stateless
+//                    work that fills the latency shadows of the recurrence -- takes the rotational
+//                    half from ring 2, and also carries the body-frame integrals (kin_body: they only
+//                    need v, w).                                                        -> ring 3
+//   warp 1 (kin)     Euler angles and world position from the (v, w) stream (kin_world); nothing
 //                    flows back to the dynamics, so this warp simply trails the dyn warp.
 //
-// The shape and every coefficient depend on the action and the substep index only; the kinematics
-// depend on (v, w) only.  Hand-off is chunk-granular (8 substeps) on named barriers -- bar.arrive by
-// the side that is done with a chunk, bar.sync by the side that needs it -- with 2 / 3 / 2 chunks
-// in flight on rings 1 / 2 / 3 (14 of the 16 hardware barriers).  The warps execute the functions of
-// run_cycle_mixed with the same fixed 32-substep grouping of the fp32 chunk sums, and every
-// operation of the loop is explicitly rounded: bit-identical with the fused kernel and the
-// three-warp kernel (tests/test_gpu_parity.py).
+// Measured stage costs for a lone warp (tools/ubench_substep.cu, cycles per substep): front 135-165,
+// the whole coefficient set 210 (hence its split), dyn 77-100, kin 82.  (A fifth warp for half of
+// the coefficient set was measured slower, 300-350 vs 250 cycles per shape-moving substep: two busy
+// warps on one sub-partition cost more than the sum of their lone times.)
+// Hand-off is chunk-granular (8 substeps) on named barriers with 3 / 2 / 2 chunks in flight on rings
+// 1 / 2 / 3 (14 of the 16 hardware barriers).  The warps execute the functions of run_cycle_mixed
+// with the same fixed 32-substep grouping of the fp32 chunk sums, and every operation is explicitly
+// rounded: bit-identical with the fused kernel (tests/test_gpu_parity.py).
 //
-// Envs may be visited through a permutation (`order`, the K-sort), and two blocks fit an SM
-// (<= 110 KB of rings each), so the kernel also serves batches of up to 64 envs per SM.
+// Envs may be visited through a permutation (`order`, the K-sort).
 #pragma once
 #include "salp_pipe_kernel.cuh"
 
 #define SALP_P4_CHUNK 8
-#define SALP_P4_NBUF1 2
-#define SALP_P4_NBUF2 3
+#define SALP_P4_NBUF1 3
+#define SALP_P4_NBUF2 2
 #define SALP_P4_NBUF3 2
 #define SALP_P4_SLOTS1 (SALP_P4_CHUNK * SALP_P4_NBUF1)
 #define SALP_P4_SLOTS2 (SALP_P4_CHUNK * SALP_P4_NBUF2)
@@ -43,20 +47,55 @@
 #define P4_FULL3(b) (1 + 2 * SALP_P4_NBUF1 + 2 * SALP_P4_NBUF2 + (b))
 #define P4_EMPTY3(b) (1 + 2 * SALP_P4_NBUF1 + 2 * SALP_P4_NBUF2 + SALP_P4_NBUF3 + (b))
 
-// dynamic shared memory: ring 2 rows are 80 bytes (axisymmetric form) or 112 bytes per lane
+// dynamic shared memory.  Rings are stored as planes of quads, [slot][quad][lane] float4, so that the
+// 32 lanes of a 128-bit access touch 512 consecutive bytes (no bank conflicts).
 template <bool AXI>
 struct P4Layout {
-  static constexpr int ROW = AXI ? 20 : SALP_PIPE_NCOEF;
-  static constexpr size_t ring2 = 0;                                                          // [SLOTS2][32][ROW] float
-  static constexpr size_t ring1 = ring2 + sizeof(float) * SALP_P4_SLOTS2 * 32 * ROW;          // [SLOTS1][32][8] float
-  static constexpr size_t ring3a = ring1 + sizeof(float) * SALP_P4_SLOTS1 * 32 * 8;           // [SLOTS3][32] float4 (v0 v1 v2 w0)
-  static constexpr size_t ring3b = ring3a + sizeof(float4) * SALP_P4_SLOTS3 * 32;             // [SLOTS3][32] float2 (w1 w2)
-  static constexpr size_t merge = ring3b + sizeof(float2) * SALP_P4_SLOTS3 * 32;              // [MERGE][32] double
-  static constexpr size_t tile = merge + sizeof(double) * SALP_P4_MERGE * 32;                 // [2][32][D] float
+  static constexpr int Q2 = AXI ? 2 : 4;                                                       // quads per ring-2 row (rotational half)
+  static constexpr size_t ring2 = 0;                                                           // [SLOTS2][Q2][32] float4
+  static constexpr size_t ring1 = ring2 + sizeof(float4) * SALP_P4_SLOTS2 * Q2 * 32;           // [SLOTS1][2][32] float4
+  static constexpr size_t ring3a = ring1 + sizeof(float4) * SALP_P4_SLOTS1 * 2 * 32;           // [SLOTS3][32] float4 (v0 v1 v2 w0)
+  static constexpr size_t ring3b = ring3a + sizeof(float4) * SALP_P4_SLOTS3 * 32;              // [SLOTS3][32] float2 (w1 w2)
+  static constexpr size_t merge = ring3b + sizeof(float2) * SALP_P4_SLOTS3 * 32;               // [MERGE][32] double
+  static constexpr size_t tile = merge + sizeof(double) * SALP_P4_MERGE * 32;                  // [2][32][D] float
 };
 static inline size_t pipe4_smem_bytes(const SalpParams& p, bool axi) {
   const size_t tile = sizeof(float) * 2 * 32 * (SALP_OBS_BASE + 2 * p.num_obstacles);
   return (axi ? P4Layout<true>::tile : P4Layout<false>::tile) + tile;
+}
+
+// Iterations j = j0..je of one hand-off chunk for the lanes whose cycle is still running (j < K),
+// WITHOUT a per-iteration lane test (a `j < K` branch inside the loop costs ~45 cycles of branch /
+// reconvergence latency per substep, as much as the arithmetic of a stage).  A full chunk in which
+// no lane ends runs unrolled as one basic block; otherwise the chunk is cut at the substeps where
+// lanes end (warp-wide min of the remaining K) and each segment runs behind ONE branch.
+// iter(j, at32): at32 = j is a multiple of the 32-substep flush interval (in an unrolled chunk only
+// its last iteration can be, so the other seven stay free of branches).
+// `dn` (warp-uniform, carried across chunks, start at 0): the first cycle end beyond the current
+// position -- recomputed by a warp reduction only after a lane has ended.  Branches are what a lone
+// warp pays for (~30 cycles each): the common chunk (full, nobody ends) costs two.
+template <class Iter>
+__device__ __forceinline__ void p4_run_chunk(int j0, int je, int K, int& dn, Iter&& iter) {
+  constexpr int C = SALP_P4_CHUNK;
+  static_assert(SALP_MIXED_CHUNK % C == 0, "flush positions must fall on the last iteration of a chunk");
+  if (dn > je && je - j0 + 1 == C) {
+    if (K > je) {
+#pragma unroll
+      for (int u = 0; u < C; u++) iter(j0 + u, u == C - 1 && (je & (SALP_MIXED_CHUNK - 1)) == 0);
+    }
+    return;
+  }
+  int a = j0;
+  while (a <= je) {
+    if (dn <= a) dn = __reduce_min_sync(0xffffffffu, K > a ? K : 0x7fffffff);
+    if (dn == 0x7fffffff) break;                                             // nobody left
+    const int e = dn - 1 < je ? dn - 1 : je;
+    if (K > a) {
+#pragma unroll 1
+      for (int j = a; j <= e; j++) iter(j, (j & (SALP_MIXED_CHUNK - 1)) == 0);
+    }
+    a = e + 1;
+  }
 }
 
 template <bool AXI>
@@ -64,10 +103,10 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
                                                 const SalpStepIO& io, uint32_t flags, const int32_t* __restrict__ order,
                                                 unsigned char* smem) {
   using L = P4Layout<AXI>;
-  constexpr int ROW = L::ROW;
+  constexpr int Q2 = L::Q2;
   constexpr int C = SALP_P4_CHUNK;
-  float* ring2 = reinterpret_cast<float*>(smem + L::ring2);
-  float* ring1 = reinterpret_cast<float*>(smem + L::ring1);
+  float4* ring2 = reinterpret_cast<float4*>(smem + L::ring2);
+  float4* ring1 = reinterpret_cast<float4*>(smem + L::ring1);
   float4* ring3a = reinterpret_cast<float4*>(smem + L::ring3a);
   float2* ring3b = reinterpret_cast<float2*>(smem + L::ring3b);
   double* merge = reinterpret_cast<double*>(smem + L::merge);
@@ -102,9 +141,14 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
   const int nch2 = (Wmax + C - 1) / C;               // chunk c = substeps c C + 1 .. (c + 1) C
   const int nch3 = Kw > 1 ? (Kw - 1 + C - 1) / C : 0;
   const float dir[3] = {(float)cx.plan.dir[0], (float)cx.plan.dir[1], (float)cx.plan.dir[2]};
+  // ring rows of substep j (planes of quads)
+  auto row1 = [&](int j) { return ring1 + (j % SALP_P4_SLOTS1) * 2 * 32 + lane; };
+  auto row2 = [&](int j) { return ring2 + (j % SALP_P4_SLOTS2) * Q2 * 32 + lane; };
 
   if (warp == 3) {
     // ---------------- front: fp64 shape chain + backward differences, j = 1..kA ----------------
+    // ring 1 has TWO readers (coefs R and dyn): a buffer is free when both have arrived (96 threads);
+    // "full" is signalled to coefs R only -- the dyn warp reads chunk c after ring 2's chunk c is full
     ShapeTrack st;
     if (K > 0) {
       Coef32 g0;
@@ -113,7 +157,7 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
     double tj = v.time_table[1];                   // carried by the same additions as the table (robot.py:674)
     int j = 1;
     for (int c = 0; c < nch2; c++) {
-      if (c >= SALP_P4_NBUF1) pipe_bar_sync(P4_EMPTY1(c % SALP_P4_NBUF1));
+      if (c >= SALP_P4_NBUF1) pipe_bar_sync(P4_EMPTY1(c % SALP_P4_NBUF1), 96);
       const int je = (c + 1) * C < Wmax ? (c + 1) * C : Wmax;
       // two updates per trip: consecutive updates are independent chains until their backward
       // differences (shape64_step carries nothing), so the scheduler overlaps them
@@ -124,18 +168,18 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
           if (j + 1 <= kA) {
             shape_front(p, dv, cx.plan, tj, j, pp.k_T0, pp.k_jet, st, f0);
             shape_front(p, dv, cx.plan, tj1, j + 1, pp.k_T0, pp.k_jet, st, f1);
-            front_store(f0, ring1 + ((j % SALP_P4_SLOTS1) * 32 + lane) * 8);
-            front_store(f1, ring1 + (((j + 1) % SALP_P4_SLOTS1) * 32 + lane) * 8);
+            front_store(f0, row1(j));
+            front_store(f1, row1(j + 1));
           } else if (j <= kA) {
             shape_front(p, dv, cx.plan, tj, j, pp.k_T0, pp.k_jet, st, f0);
-            front_store(f0, ring1 + ((j % SALP_P4_SLOTS1) * 32 + lane) * 8);
+            front_store(f0, row1(j));
           }
           tj = rn::dadd(tj1, p.dt);
           j += 2;
         } else {
           if (j <= kA) {
             shape_front(p, dv, cx.plan, tj, j, pp.k_T0, pp.k_jet, st, f0);
-            front_store(f0, ring1 + ((j % SALP_P4_SLOTS1) * 32 + lane) * 8);
+            front_store(f0, row1(j));
           }
           tj = tj1;
           j += 1;
@@ -152,40 +196,31 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
       merge[8 * 32 + lane] = b.com_acc;
     }
   } else if (warp == 2) {
-    // ---------------- coefs: the stateless fp32 coefficient set of each ShapeFront ----------------
+    // ---------------- coefs R: the rotational half of the coefficient set of each ShapeFront ----------------
+    auto one = [&](int j) {
+      ShapeFront f;
+      Coef32 g;
+      front_load(f, row1(j));
+      make_coefs_R<AXI>(dv, dir, f, g);
+      coef_store_R<AXI>(g, row2(j));
+    };
     int j = 1;
     for (int c = 0; c < nch2; c++) {
       pipe_bar_sync(P4_FULL1(c % SALP_P4_NBUF1));
       if (c >= SALP_P4_NBUF2) pipe_bar_sync(P4_EMPTY2(c % SALP_P4_NBUF2));
       const int je = (c + 1) * C < Wmax ? (c + 1) * C : Wmax;
-      while (j <= je) {
-        ShapeFront f0, f1;
-        Coef32 g0, g1;
+      while (j <= je) {                            // two updates per trip (independent chains)
         if (j + 1 <= je) {
-          if (j + 1 <= kA) {
-            front_load(f0, ring1 + ((j % SALP_P4_SLOTS1) * 32 + lane) * 8);
-            front_load(f1, ring1 + (((j + 1) % SALP_P4_SLOTS1) * 32 + lane) * 8);
-            make_coefs<AXI>(dv, dir, f0, g0);
-            make_coefs<AXI>(dv, dir, f1, g1);
-            coef_store<AXI>(g0, ring2 + ((j % SALP_P4_SLOTS2) * 32 + lane) * ROW);
-            coef_store<AXI>(g1, ring2 + (((j + 1) % SALP_P4_SLOTS2) * 32 + lane) * ROW);
-          } else if (j <= kA) {
-            front_load(f0, ring1 + ((j % SALP_P4_SLOTS1) * 32 + lane) * 8);
-            make_coefs<AXI>(dv, dir, f0, g0);
-            coef_store<AXI>(g0, ring2 + ((j % SALP_P4_SLOTS2) * 32 + lane) * ROW);
-          }
+          if (j + 1 <= kA) { one(j); one(j + 1); }
+          else if (j <= kA) one(j);
           j += 2;
         } else {
-          if (j <= kA) {
-            front_load(f0, ring1 + ((j % SALP_P4_SLOTS1) * 32 + lane) * 8);
-            make_coefs<AXI>(dv, dir, f0, g0);
-            coef_store<AXI>(g0, ring2 + ((j % SALP_P4_SLOTS2) * 32 + lane) * ROW);
-          }
+          if (j <= kA) one(j);
           j += 1;
         }
       }
       __syncwarp();
-      pipe_bar_arrive(P4_EMPTY1(c % SALP_P4_NBUF1));
+      pipe_bar_arrive(P4_EMPTY1(c % SALP_P4_NBUF1), 96);
       pipe_bar_arrive(P4_FULL2(c % SALP_P4_NBUF2));
     }
   } else if (warp == 1) {
@@ -202,19 +237,18 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
       mixed_init_kin(b, s);
       dyn_step<false, false, AXI>(dv, g, s);
     }
+    // iteration j: kin step j - 1 on the (v, w) in registers, then the (v, w) of step j from the ring
+    auto kin_iter = [&](int j, bool at32) {
+      const float4 a = ring3a[(j % SALP_P4_SLOTS3) * 32 + lane];
+      const float2 bb = ring3b[(j % SALP_P4_SLOTS3) * 32 + lane];
+      kin_world(dv, s);
+      if (at32) flush_world(b, s);
+      s.v0 = a.x; s.v1 = a.y; s.v2 = a.z; s.w0 = a.w; s.w1 = bb.x; s.w2 = bb.y;
+    };
+    int dn = 0;
     for (int c = 0; c < nch3; c++) {
       pipe_bar_sync(P4_FULL3(c % SALP_P4_NBUF3));
-      const int je = (c + 1) * C < Kw - 1 ? (c + 1) * C : Kw - 1;
-#pragma unroll 1
-      for (int j = c * C + 1; j <= je; j++) {
-        if (j < K) {
-          kin_world(dv, s);                                     // step j - 1, on the (v, w) loaded one trip earlier
-          if ((j & (SALP_MIXED_CHUNK - 1)) == 0) flush_world(b, s);
-          const float4 a = ring3a[(j % SALP_P4_SLOTS3) * 32 + lane];
-          const float2 bb = ring3b[(j % SALP_P4_SLOTS3) * 32 + lane];
-          s.v0 = a.x; s.v1 = a.y; s.v2 = a.z; s.w0 = a.w; s.w1 = bb.x; s.w2 = bb.y;
-        }
-      }
+      p4_run_chunk(c * C + 1, (c + 1) * C < Kw - 1 ? (c + 1) * C : Kw - 1, K, dn, kin_iter);
       __syncwarp();
       pipe_bar_arrive(P4_EMPTY3(c % SALP_P4_NBUF3));
     }
@@ -236,40 +270,75 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
       s.pos0 = s.pos1 = s.pos2 = 0.f; s.ang0 = s.ang1 = s.ang2 = 0.f;
       dyn_step<false, false, AXI>(dv, g, s);
     }
-    const int nch = nch2 > nch3 ? nch2 : nch3;
-    for (int c = 0; c < nch; c++) {
-      if (c < nch2) pipe_bar_sync(P4_FULL2(c % SALP_P4_NBUF2));
-      if (c < nch3 && c >= SALP_P4_NBUF3) pipe_bar_sync(P4_EMPTY3(c % SALP_P4_NBUF3));
-      const int je = (c + 1) * C < Kw - 1 ? (c + 1) * C : Kw - 1;
-      if (c * C + 1 <= WA) {
-        // the shape is (or may still be) moving somewhere in this chunk: coefficients from ring 2
-#pragma unroll 1
-        for (int j = c * C + 1; j <= je; j++) {
-          if (j < K) {
-            if (j <= WA) coef_load<AXI>(g, ring2 + ((j % SALP_P4_SLOTS2) * 32 + lane) * ROW);
-            kin_body(dv, s);                                    // step j - 1
-            dyn_step<false, false, AXI>(dv, g, s);              // (j > W: com_rate = com_acc = 0, same bits as the static form)
-            ring3a[(j % SALP_P4_SLOTS3) * 32 + lane] = make_float4(s.v0, s.v1, s.v2, s.w0);
-            ring3b[(j % SALP_P4_SLOTS3) * 32 + lane] = make_float2(s.w1, s.w2);
-            if ((j & (SALP_MIXED_CHUNK - 1)) == 0) flush_body(b, s);
-          }
-        }
-      } else {
-        // the coast: static shape, coefficients stay in registers
-#pragma unroll 1
-        for (int j = c * C + 1; j <= je; j++) {
-          if (j < K) {
-            kin_body(dv, s);
-            dyn_step<false, true, AXI>(dv, g, s);
-            ring3a[(j % SALP_P4_SLOTS3) * 32 + lane] = make_float4(s.v0, s.v1, s.v2, s.w0);
-            ring3b[(j % SALP_P4_SLOTS3) * 32 + lane] = make_float2(s.w1, s.w2);
-            if ((j & (SALP_MIXED_CHUNK - 1)) == 0) flush_body(b, s);
-          }
-        }
-      }
+    // g_j: translational half computed here from the ShapeFront (independent of the motion state: it
+    // fills the latency shadows of the recurrence), rotational half from ring 2
+    auto coefs_of = [&](int j) {
+      ShapeFront f;
+      front_load(f, row1(j));
+      coef_load_R<AXI>(g, row2(j));
+      make_coefs_T<AXI>(dv, dir, f, g);
+    };
+    auto hand_over = [&](int j) {
+      ring3a[(j % SALP_P4_SLOTS3) * 32 + lane] = make_float4(s.v0, s.v1, s.v2, s.w0);
+      ring3b[(j % SALP_P4_SLOTS3) * 32 + lane] = make_float2(s.w1, s.w2);
+    };
+    // iteration j: body-frame integrals of step j - 1, dynamics of substep j, (v, w) of step j to the ring
+    auto dyn_iter_load = [&](int j, bool at32) {         // the shape is moving
+      coefs_of(j);
+      kin_body(dv, s);
+      dyn_step<false, false, AXI>(dv, g, s);
+      hand_over(j);
+      if (at32) flush_body(b, s);
+    };
+    auto dyn_iter_moving = [&](int j, bool at32) {       // the one chunk in which the warp's shape motion ends (W)
+      if (j <= WA) coefs_of(j);
+      kin_body(dv, s);
+      dyn_step<false, false, AXI>(dv, g, s);            // (j > W: com_rate = com_acc = 0, same bits as the static form)
+      hand_over(j);
+      if (at32) flush_body(b, s);
+    };
+    auto dyn_iter_static = [&](int j, bool at32) {       // the coast: coefficients stay in registers
+      kin_body(dv, s);
+      dyn_step<false, true, AXI>(dv, g, s);
+      hand_over(j);
+      if (at32) flush_body(b, s);
+    };
+    // Three loops instead of one with per-chunk conditions (a lone warp pays ~30 cycles per branch):
+    //   A  chunks whose substeps all use fresh coefficients (the shape moves),
+    //   W  the chunks up to nch2 (the one in which the warp's shape motion ends; producers' last chunk),
+    //   B  the coast: coefficients stay in registers, only ring 3 is fed.
+    int dn = 0;
+    int c = 0;
+    auto chunk_end = [&](int cc) { return (cc + 1) * C < Kw - 1 ? (cc + 1) * C : Kw - 1; };
+    const int nA = WA / C < nch3 ? WA / C : nch3;              // chunks with je <= WA (and ring-3 traffic)
+    for (; c < nA; c++) {
+      pipe_bar_sync(P4_FULL2(c % SALP_P4_NBUF2));              // (ring 1 chunk c was full before ring 2 chunk c)
+      if (c >= SALP_P4_NBUF3) pipe_bar_sync(P4_EMPTY3(c % SALP_P4_NBUF3));
+      p4_run_chunk(c * C + 1, (c + 1) * C, K, dn, dyn_iter_load);
       __syncwarp();
-      if (c < nch2) pipe_bar_arrive(P4_EMPTY2(c % SALP_P4_NBUF2));
+      pipe_bar_arrive(P4_EMPTY1(c % SALP_P4_NBUF1), 96);
+      pipe_bar_arrive(P4_EMPTY2(c % SALP_P4_NBUF2));
+      pipe_bar_arrive(P4_FULL3(c % SALP_P4_NBUF3));
+    }
+    for (; c < nch2; c++) {
+      pipe_bar_sync(P4_FULL2(c % SALP_P4_NBUF2));
+      if (c < nch3 && c >= SALP_P4_NBUF3) pipe_bar_sync(P4_EMPTY3(c % SALP_P4_NBUF3));
+      p4_run_chunk(c * C + 1, chunk_end(c), K, dn, dyn_iter_moving);
+      __syncwarp();
+      pipe_bar_arrive(P4_EMPTY1(c % SALP_P4_NBUF1), 96);
+      pipe_bar_arrive(P4_EMPTY2(c % SALP_P4_NBUF2));
       if (c < nch3) pipe_bar_arrive(P4_FULL3(c % SALP_P4_NBUF3));
+    }
+    for (; c < nch3 && c < SALP_P4_NBUF3; c++) {               // (only when the shape motion ends within the first chunks)
+      p4_run_chunk(c * C + 1, chunk_end(c), K, dn, dyn_iter_static);
+      __syncwarp();
+      pipe_bar_arrive(P4_FULL3(c % SALP_P4_NBUF3));
+    }
+    for (; c < nch3; c++) {
+      pipe_bar_sync(P4_EMPTY3(c % SALP_P4_NBUF3));
+      p4_run_chunk(c * C + 1, chunk_end(c), K, dn, dyn_iter_static);
+      __syncwarp();
+      pipe_bar_arrive(P4_FULL3(c % SALP_P4_NBUF3));
     }
     if (K > 0) {
       kin_body(dv, s);                                          // step K - 1
@@ -308,7 +377,7 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
   }
 }
 
-__global__ void __launch_bounds__(SALP_P4_THREADS, 2)
+__global__ void __launch_bounds__(SALP_P4_THREADS, 1)
 salp_step_kernel_pipe4(const __grid_constant__ SalpParams p, const __grid_constant__ SalpDerived dv,
                        const __grid_constant__ SalpView v, const __grid_constant__ SalpStepIO io, uint32_t flags,
                        const int32_t* __restrict__ order) {

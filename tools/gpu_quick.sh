@@ -1,0 +1,5 @@
+#!/bin/bash
+# quick GPU check: pipeline-kernel parity tests + small-batch timings
+timeout 200 python -m pytest tests/test_gpu_parity.py -q -x -k "pipeline or shard or axisym or per_step" 2>&1 | tail -5
+timeout 100 python tools/diag_phases.py
+timeout 200 python bench.py --steps 60 --warmup 5 --no-cpu-baseline --no-sweep | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(\"bench\", d[\"value\"], d[\"ms_per_step\"], d[\"e2e\"][\"value\"])"
