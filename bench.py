@@ -18,7 +18,14 @@ ranks (all-reduce MAX).  e2e = the same workload through the host-buffer C-ABI c
 (salp_step_host: pinned host actions -> H2D -> kernel -> D2H of obs/reward/flags/terminal obs,
 one stream sync), wall-clocked around K synchronous calls.
 
-roofline: the dominant (only) kernel is salp_step_kernel<MIXED>; it is bound by the FP32 SIMT
+cpu_baseline / --impl reference: the reference's OWN CPU path -- the unmodified Python SalpRobotEnv
+under a SubprocVecEnv-equivalent (oracle/ref_vecenv.py: one process per host core, pipes, lock-step,
+worker-side auto-reset; src/train_robot.py:25-26) -- when its sources are staged (baseline/_ref/src,
+tools/stage_reference.py) and numba is importable; the plain-C port (oracle/salp_oracle.c) is timed
+beside it (`cpu_baseline_port`) and is the fallback.
+
+roofline: the dominant (only significant) kernel is the step kernel the library reports
+(salp_last_step_kernel); it is bound by the FP32 SIMT
 pipe, not HBM and not tensor cores (~0.66 KB of state traffic against ~3.5e5 flop
 per env-step), so `bound` is "fp32" and `achieved` = substeps/s * 500 flop (SURVEY 8d's
 canonical per-substep count of the reference formulation) against the FFMA rate this same run
@@ -41,7 +48,16 @@ sys.path.insert(0, ROOT)
 FLOP_PER_SUBSTEP = 500.0            # SURVEY.md 8(d) "ALGORITHMIC work per unit"
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 METRIC = "env-steps/sec"
-WORKLOAD = "4096 batched envs per GPU, uniform-random Box actions, auto-reset, 1 cycle (0..1348 substeps) per env-step"
+
+
+def workload(n):
+    return f"{n} batched envs per GPU, uniform-random Box actions, auto-reset, 1 cycle (0..1348 substeps) per env-step"
+
+
+def common_config(n, gpus):
+    """Identical in both arms (the driver compares the two lines' `config`)."""
+    return {"workload": workload(n), "envs_per_gpu": n, "global_envs": n * gpus,
+            "actions": "uniform Box (SURVEY 8d input A)", "auto_reset": True, "parallelism": f"env-shard x{gpus}"}
 
 
 def parse_args():
@@ -118,9 +134,9 @@ def host_cores():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_baseline(seconds, total_envs=4096):
-    """Bounded sample of the same workload on the host cores: `total_envs` envs split over one
-    process per core, as many vectorised steps as fit in ~`seconds`."""
+def port_baseline(seconds, total_envs=4096):
+    """The plain-C port on the host cores: `total_envs` envs split over one process per core, as many
+    vectorised steps as fit in ~`seconds`."""
     cores = host_cores()
     per = max(1, total_envs // cores)
     arm = CpuArm(cores, per)
@@ -134,8 +150,44 @@ def cpu_baseline(seconds, total_envs=4096):
     return {"value": n / dt, "unit": METRIC, "cores": cores, "kind": "port",
             "substeps_per_sec": sub / dt, "mean_substeps": sub / n,
             "sample": f"{per * cores} envs ({per}/process x {cores} processes) x {steps} vectorised steps of the "
-                      f"same workload, oracle/salp_oracle.c (gcc -O2 scalar float64 port of the reference's Python; "
-                      f"the reference's own numpy/numba path measured 3.15 env-steps/s/core in SURVEY.md section 6)"}
+                      f"same workload, oracle/salp_oracle.c (gcc -O2 scalar float64 port of the reference's Python)"}
+
+
+def reference_available():
+    try:
+        from oracle import ref_harness
+        return ref_harness.available()
+    except Exception:
+        return False
+
+
+def reference_baseline(vec_steps, warmup, n_envs=None):
+    """The reference's own CPU path: unmodified Python SalpRobotEnv x `cores`, one process each,
+    lock-step vector steps (SubprocVecEnv semantics, src/train_robot.py:25-26)."""
+    from oracle import ref_vecenv
+    cores = n_envs or host_cores()
+    n, sub, dt = ref_vecenv.time_reference(cores, vec_steps, warmup)
+    return {"value": n / dt, "unit": METRIC, "cores": cores, "kind": "reference", "seconds": dt,
+            "substeps_per_sec": sub / dt, "mean_substeps": sub / max(n, 1),
+            "sample": f"{cores} envs (1 per process, {cores} processes, pipes, lock-step) x {vec_steps} vector steps after "
+                      f"{warmup} warm-up steps (numba JIT done before the fork) of the same workload: the UNMODIFIED "
+                      f"Python reference (SalpRobotEnv under a SubprocVecEnv-equivalent, oracle/ref_vecenv.py)",
+            "reference_files": ref_vecenv.manifest()}
+
+
+def cpu_baseline(seconds, total_envs=4096):
+    """`cpu_baseline` of the CUDA arm's line: the reference's own path if its sources travelled
+    (kind "reference", ~`seconds` of lock-step vector steps), the C port beside it."""
+    port = port_baseline(seconds, total_envs)
+    if reference_available():
+        try:
+            ref = reference_baseline(vec_steps=max(10, int(seconds / 0.55)), warmup=3)
+            return ref, port
+        except Exception as e:       # e.g. numba missing on the box: say so, fall back
+            port["reference_unavailable"] = f"{type(e).__name__}: {e}"
+    else:
+        port["reference_unavailable"] = "reference sources not staged (tools/stage_reference.py) or numba missing"
+    return port, None
 
 
 def run_reference_arm(args):
@@ -143,31 +195,46 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = host_cores()
-    # bounded per-step sample: size the per-step env count so that (K + W) steps take ~2 minutes
-    probe = CpuArm(cores, 8)
-    probe.run(1)
-    n, _, dt = probe.run(2)
-    probe.close()
-    rate = n / dt
-    budget = 120.0 / max(1, args.steps + args.warmup)
-    per = int(max(1, min(4096 // cores, rate * budget / cores)))
-    arm = CpuArm(cores, per)
-    try:
-        arm.run(max(1, args.warmup))
-        n, sub, dt = arm.run(args.steps)
-    finally:
-        arm.close()
-    value = n / dt
+    n = args.envs
+    base = None
+    if reference_available():
+        # one bench "step" = R lock-step vector steps of `cores` reference envs (a bounded sample of the
+        # n-env batch); R sized so that (K + W) steps stay within ~2 minutes (a vector step waits for
+        # its slowest env: ~0.55 s)
+        R = max(1, min(3, int(120.0 / (0.55 * max(1, args.steps + args.warmup)))))
+        try:
+            base = reference_baseline(vec_steps=args.steps * R, warmup=max(3, args.warmup * R))
+            base["sample"] = f"each step = {R} lock-step vector step(s); " + base["sample"]
+        except Exception as e:
+            base = None
+            sys.stderr.write(f"reference arm: Python reference failed ({type(e).__name__}: {e}); timing the C port\n")
+    if base is None:
+        # fallback: the C port; bounded per-step sample sized so that (K + W) steps take ~2 minutes
+        probe = CpuArm(cores, 8)
+        probe.run(1)
+        m, _, dt = probe.run(2)
+        probe.close()
+        rate = m / dt
+        budget = 120.0 / max(1, args.steps + args.warmup)
+        per = int(max(1, min(max(1, n // cores), rate * budget / cores)))
+        arm = CpuArm(cores, per)
+        try:
+            arm.run(max(1, args.warmup))
+            m, sub, dt = arm.run(args.steps)
+        finally:
+            arm.close()
+        base = {"value": m / dt, "unit": METRIC, "cores": cores, "kind": "port", "seconds": dt, "substeps_per_sec": sub / dt,
+                "sample": f"each step = {per * cores} envs ({per}/process x {cores} processes) of the workload; "
+                          "oracle/salp_oracle.c, the plain-C float64 port (reference sources not staged or numba missing)"}
+    value = base["value"]
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "impl": "reference", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * base["seconds"] / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_step": per * cores, "actions": "uniform Box", "auto_reset": True},
-        "cpu_baseline": {"value": value, "unit": METRIC, "cores": cores, "kind": "port",
-                         "sample": f"each step = {per * cores} envs ({per}/process x {cores} processes) of the workload; "
-                                   "oracle/salp_oracle.c, the plain-C float64 port of the reference's Python path "
-                                   "(the Python reference itself cannot travel to the GPU box)"},
-        "substeps_per_sec": sub / dt,
+        "config": common_config(n, args.gpus),
+        "cpu_baseline": base,
+        "substeps_per_sec": base["substeps_per_sec"],
         "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -329,6 +396,7 @@ def run_cuda_arm(args):
     barrier()
     clocks = sampler.stop()
     batch.check()
+    step_kernel_name = batch.last_step_kernel          # what the launcher picked (salp_last_step_kernel)
     ms = max_over_ranks(ms)
     total_env_steps = sum_over_ranks(float(n * args.steps))
     total_substeps = sum_over_ranks(float(substeps))
@@ -388,6 +456,22 @@ def run_cuda_arm(args):
                    "fp32_tflops_per_gpu": ssum / world / (m * 1e-3) * FLOP_PER_SUBSTEP / 1e12}
             if fp32_peak:
                 row["frac_of_measured_fp32"] = row["fp32_tflops_per_gpu"] / fp32_peak
+            row["kernel"] = b.last_step_kernel
+            if not args.no_e2e:      # the same rows through salp_step_host (page-locked host buffers, wall clock)
+                b.reset()
+                ha = [b.host_buffer((ne, 3), np.float32) for _ in range(2)]
+                ph = p[:2].cpu().numpy()
+                ha[0][:] = ph[0]
+                ha[1][:] = ph[1]
+                for k in range(3):
+                    b.step(ha[k % 2], auto_reset=True, sort_by_k=sort_flag(ne), extras=False)
+                es = max(5, st // 2)
+                barrier()
+                t0 = time.perf_counter()
+                for k in range(es):
+                    b.step(ha[k % 2], auto_reset=True, sort_by_k=sort_flag(ne), extras=False)
+                dt_h = max_over_ranks(time.perf_counter() - t0)
+                row["e2e_env_steps_per_sec"] = sum_over_ranks(float(ne * es)) / dt_h
             sweep.append(row)
             b.close()
             del b, p
@@ -419,9 +503,9 @@ def run_cuda_arm(args):
             b.close()
             del b, p
 
-    cpu = None
+    cpu = cpu_port = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(args.cpu_seconds, total_envs=n)
+        cpu, cpu_port = cpu_baseline(args.cpu_seconds, total_envs=n)
 
     if rank == 0:
         peak = fp32_peak or NOMINAL_FP32_TFLOPS
@@ -429,17 +513,17 @@ def run_cuda_arm(args):
             "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if prec == PRECISION_MIXED else "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": n, "global_envs": n * world,
-                       "precision": args.precision, "sort_by_k": sort_flag(n), "l2": "flushed between timed steps "
-                       "(256 MiB memset outside the per-step event pairs)", "parallelism": f"env-shard x{world}"},
+            "config": common_config(n, world),
+            "config_detail": {"precision": args.precision, "sort_by_k": sort_flag(n), "l2": "flushed between timed steps "
+                              "(256 MiB memset outside the per-step event pairs)"},
             "substeps_per_sec": sub_rate, "mean_substeps_per_env_step": total_substeps / total_env_steps,
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak, "traffic": ncu_traffic(n, args.precision),
+                         "traffic_source": "profiles/traffic.json (ncu --set full capture of this workload, committed; not measured in this run)",
                          "peak_source": ("measured in this run: salp_probe_fp32_peak (FFMA, 2048 thr/SM)"
                                          if fp32_peak else "nominal"),
                          "nominal_peak": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved_tf / NOMINAL_FP32_TFLOPS,
-                         "flop_per_substep": FLOP_PER_SUBSTEP, "kernel": ("salp_step_kernel<F64>" if prec != PRECISION_MIXED else
-                                    "salp_step_kernel_pipe" if n <= 32 * 148 and not sort_flag(n) else "salp_step_kernel_lat<MIXED>"),
+                         "flop_per_substep": FLOP_PER_SUBSTEP, "kernel": step_kernel_name,
                          "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": hbm_achieved / hbm_peak, "bytes_per_env_step": bytes_per_env_step,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
@@ -449,6 +533,8 @@ def run_cuda_arm(args):
             line["e2e"] = e2e
         if cpu:
             line["cpu_baseline"] = cpu
+        if cpu_port:
+            line["cpu_baseline_port"] = cpu_port
         if sweep:
             line["sweep"] = sweep
         if input_b:

@@ -8,9 +8,11 @@ installed in this image (gymnasium, pygame, matplotlib, PIL).  It exists so that
     (tools/gen_golden.py), and
   * oracle/salp_oracle.c (the C restatement) can be pinned against the reference.
 
-It only works where /root/reference (or $SALP_REF_DIR) exists, i.e. in the build
-container.  Nothing under grasp_lab_salp_b200/ imports this file, and nothing that
-runs on the GPU box (pytest -m gpu, smoke(), bench.py) needs it.
+The reference is looked for in $SALP_REF_DIR, then baseline/_ref/src (staged by
+tools/stage_reference.py: git-ignored, but it travels to the GPU box with the gpurun snapshot, so
+bench.py can time the real reference there), then /root/reference/src (build container only).
+Nothing under grasp_lab_salp_b200/ imports this file; of what runs on the GPU box only bench.py's
+CPU legs use it (pytest -m gpu and smoke() do not).
 """
 from __future__ import annotations
 
@@ -21,12 +23,16 @@ import types
 import numpy as np
 
 REF_ENV_VAR = "SALP_REF_DIR"
-DEFAULT_REF = "/root/reference/src"
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SEARCH = (os.path.join(_REPO, "baseline", "_ref", "src"), "/root/reference/src")
 
 
 def reference_dir() -> str | None:
-    d = os.environ.get(REF_ENV_VAR, DEFAULT_REF)
-    return d if os.path.isfile(os.path.join(d, "salp_robot_env.py")) else None
+    cands = ([os.environ[REF_ENV_VAR]] if os.environ.get(REF_ENV_VAR) else []) + list(SEARCH)
+    for d in cands:
+        if os.path.isfile(os.path.join(d, "salp_robot_env.py")):
+            return d
+    return None
 
 
 def available() -> bool:

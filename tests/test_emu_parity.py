@@ -6,7 +6,7 @@ import pytest
 from emu_backend import EmuBatch, emu_cdll, emu_lane_cdll
 from grasp_lab_salp_b200 import PRECISION_F64, PRECISION_MIXED
 from oracle.salp_oracle import OracleVecEnv
-from parity import check_blowup_golden, TOL_F64, TOL_MIXED, TOL_MIXED_FREE_RUN, golden_params, lockstep_compare, sample_scene_pool, load_golden, replay_golden
+from parity import check_blowup_golden, TOL_F64, MIXED_FLOORS, TOL_MIXED, TOL_MIXED_FREE_RUN, golden_params, lockstep_compare, sample_scene_pool, load_golden, replay_golden
 
 GOLDENS = ["ref_fixed10.npz", "ref_edge.npz", "ref_random.npz", "ref_clipped.npz"]
 
@@ -54,7 +54,7 @@ def test_emu_mixed_per_step_tolerance_vs_oracle(kind):
     else:
         acts = np.clip(rng.normal(size=(T, n, 3)), [0, 0, -1], [1, 1, 1]).astype(np.float32)
     report = {}
-    lockstep_compare(prod, orc, acts, resync=True, rtol=TOL_MIXED["rtol"], floor=TOL_MIXED["floor"], report=report)
+    lockstep_compare(prod, orc, acts, resync=True, rtol=TOL_MIXED["rtol"], floor=TOL_MIXED["floor"], floors=MIXED_FLOORS, report=report)
     print(kind, report)
 
 
@@ -134,7 +134,7 @@ def test_other_obstacle_counts(num_obstacles):
     assert prod.obs_dim == 6 + 2 * num_obstacles
     acts = np.random.default_rng(3).uniform([0, 0, -1], [1, 1, 1], size=(T, n, 3)).astype(np.float32)
     lockstep_compare(prod, orc, acts, resync=True, rtol=TOL_MIXED["rtol"], floor=TOL_MIXED["floor"],
-                     num_obstacles=num_obstacles)
+                     floors=MIXED_FLOORS, num_obstacles=num_obstacles)
 
 
 def test_non_default_robot_parameters():

@@ -6,7 +6,7 @@ import pytest
 
 from grasp_lab_salp_b200 import PRECISION_F64, PRECISION_MIXED, SalpBatch
 from oracle.salp_oracle import OracleVecEnv
-from parity import (check_blowup_golden, TOL_F64, TOL_MIXED, TOL_MIXED_FREE_RUN, golden_params, load_golden, lockstep_compare,
+from parity import (check_blowup_golden, TOL_F64, MIXED_FLOORS, TOL_MIXED, TOL_MIXED_FREE_RUN, golden_params, load_golden, lockstep_compare,
                     replay_golden, sample_scene_pool)
 
 pytestmark = pytest.mark.gpu
@@ -63,7 +63,7 @@ def test_mixed_per_step_tolerance_vs_oracle(kind):
     rng = np.random.default_rng(11)
     acts = uniform_actions(rng, T, n) if kind == "uniform" else clipped_actions(rng, T, n)
     report = {}
-    lockstep_compare(prod, orc, acts, resync=True, rtol=TOL_MIXED["rtol"], floor=TOL_MIXED["floor"], report=report)
+    lockstep_compare(prod, orc, acts, resync=True, rtol=TOL_MIXED["rtol"], floor=TOL_MIXED["floor"], floors=MIXED_FLOORS, report=report)
     prod.check()
     print(kind, report)
 
@@ -350,7 +350,7 @@ def test_pipeline_kernel_short_cycles_and_chunk_boundaries():
     np.testing.assert_array_equal(probe.substeps[:m], ks)          # the crafted coasts give K = 0, 1, 2, ...
     report = {}
     lockstep_compare(prod, orc, np.repeat(acts[None], 3, axis=0), resync=True, rtol=TOL_MIXED["rtol"],
-                     floor=TOL_MIXED["floor"], report=report)
+                     floor=TOL_MIXED["floor"], floors=MIXED_FLOORS, report=report)
     prod.check()
     print(report)
     pipe, fused = SalpBatch(n, prod.params, seed=4), SalpBatch(n, prod.params, seed=4)
@@ -374,7 +374,7 @@ def test_other_obstacle_count_and_masked_device_reset():
     orc = OracleVecEnv(n, params, seed=7, threads=1)
     assert prod.obs_dim == 16
     acts = uniform_actions(np.random.default_rng(3), T, n)
-    lockstep_compare(prod, orc, acts, resync=True, rtol=TOL_MIXED["rtol"], floor=TOL_MIXED["floor"], num_obstacles=5)
+    lockstep_compare(prod, orc, acts, resync=True, rtol=TOL_MIXED["rtol"], floor=TOL_MIXED["floor"], floors=MIXED_FLOORS, num_obstacles=5)
     mask = np.zeros(n, np.uint8)
     mask[::7] = 1
     obs_o = orc.reset(mask).copy()
