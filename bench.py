@@ -177,16 +177,24 @@ def reference_baseline(vec_steps, warmup, n_envs=None):
 
 def cpu_baseline(seconds, total_envs=4096):
     """`cpu_baseline` of the CUDA arm's line: the reference's own path if its sources travelled
-    (kind "reference", ~`seconds` of lock-step vector steps), the C port beside it."""
+    (kind "reference", ~`seconds` of lock-step vector steps), the C port beside it.  The reference
+    runs in a FRESH interpreter (this file with --impl reference): numba's LAPACK binding failed to
+    import inside a process that had already initialised torch + CUDA on the GPU box."""
+    import subprocess
     port = port_baseline(seconds, total_envs)
-    if reference_available():
-        try:
-            ref = reference_baseline(vec_steps=max(10, int(seconds / 0.55)), warmup=3)
-            return ref, port
-        except Exception as e:       # e.g. numba missing on the box: say so, fall back
-            port["reference_unavailable"] = f"{type(e).__name__}: {e}"
-    else:
+    if not reference_available():
         port["reference_unavailable"] = "reference sources not staged (tools/stage_reference.py) or numba missing"
+        return port, None
+    steps = max(4, int(seconds / (3 * 0.55)))
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps),
+                            "--warmup", "1", "--envs", str(total_envs)], capture_output=True, text=True, timeout=600)
+        ref = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        if ref.get("kind") == "reference":
+            return ref, port
+        port["reference_unavailable"] = "the reference arm fell back to the port: " + r.stderr.strip().splitlines()[-1][:300]
+    except Exception as e:
+        port["reference_unavailable"] = f"{type(e).__name__}: {e}"
     return port, None
 
 
@@ -206,7 +214,9 @@ def run_reference_arm(args):
             base = reference_baseline(vec_steps=args.steps * R, warmup=max(3, args.warmup * R))
             base["sample"] = f"each step = {R} lock-step vector step(s); " + base["sample"]
         except Exception as e:
+            import traceback
             base = None
+            traceback.print_exc()
             sys.stderr.write(f"reference arm: Python reference failed ({type(e).__name__}: {e}); timing the C port\n")
     if base is None:
         # fallback: the C port; bounded per-step sample sized so that (K + W) steps take ~2 minutes

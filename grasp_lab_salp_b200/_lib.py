@@ -12,9 +12,9 @@ import os
 from .params import SalpParams
 
 OK = 0
-ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_RANGE, ERR_ALLOC = -1, -2, -3, -4, -5
+ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_RANGE, ERR_ALLOC, ERR_HANDOFF = -1, -2, -3, -4, -5, -6
 _ERR_NAMES = {ERR_INVALID: "SALP_ERR_INVALID", ERR_CUDA: "SALP_ERR_CUDA", ERR_NO_DEVICE: "SALP_ERR_NO_DEVICE",
-              ERR_RANGE: "SALP_ERR_RANGE", ERR_ALLOC: "SALP_ERR_ALLOC"}
+              ERR_RANGE: "SALP_ERR_RANGE", ERR_ALLOC: "SALP_ERR_ALLOC", ERR_HANDOFF: "SALP_ERR_HANDOFF"}
 
 
 class SalpError(RuntimeError):

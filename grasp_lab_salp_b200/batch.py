@@ -21,7 +21,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .params import (NUM_EPISODE_METRICS, NUM_REWARD_TERMS, STEP_AUTORESET, STEP_FUSED, STEP_GENERIC, STEP_PIPELINE, STEP_SORT_BY_K, SalpParams,
+from .params import (NUM_EPISODE_METRICS, NUM_REWARD_TERMS, STEP_AUTORESET, STEP_CHECK_HANDOFF, STEP_FUSED, STEP_GENERIC, STEP_PIPELINE, STEP_SORT_BY_K, SalpParams,
                      default_params, field_dtype, field_id)
 
 
@@ -135,7 +135,7 @@ class SalpBatch:
         return self.obs
 
     def step(self, actions, auto_reset: bool = False, sort_by_k: bool = False, extras: bool = True,
-             pipeline=None, generic: bool = False):
+             pipeline=None, generic: bool = False, check_handoff: bool = False):
         a = actions
         if not (type(a) is np.ndarray and a.dtype == np.float32 and a.flags.c_contiguous):
             a = np.ascontiguousarray(actions, np.float32)
@@ -159,7 +159,7 @@ class SalpBatch:
         io.actions = a.__array_interface__["data"][0]
         flags = ((STEP_AUTORESET if auto_reset else 0) | (STEP_SORT_BY_K if sort_by_k else 0)
                  | (0 if pipeline is None else (STEP_PIPELINE if pipeline else STEP_FUSED))
-                 | (STEP_GENERIC if generic else 0))
+                 | (STEP_GENERIC if generic else 0) | (STEP_CHECK_HANDOFF if check_handoff else 0))
         rc = self._L.salp_step_host(self._h, self._io_host_ref, flags)
         if rc != 0:
             self._check(rc)

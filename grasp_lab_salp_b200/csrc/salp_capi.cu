@@ -506,6 +506,7 @@ int salp_check(salp_handle h) {
   int32_t st = 0;
   CU(h, cudaMemcpy(&st, h->view.status, sizeof st, cudaMemcpyDeviceToHost));
   if (st == SALP_ERR_RANGE) return fail(h, st, "an action drove a cycle past SALP_MAX_SUBSTEPS (non-finite or out-of-Box action)");
+  if (st == SALP_ERR_HANDOFF) return fail(h, st, "pipeline kernel: a warp read a ring row that was not written for it (hand-off race)");
   if (st != 0) return fail(h, st, "device-side error");
   return SALP_OK;
 }

@@ -140,13 +140,18 @@ int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& i
     if (dev < 0 || dev >= 64 || !configured4[dev]) {
       SalpParams widest = p;
       widest.num_obstacles = SALP_MAX_OBSTACLES;
-      if (cudaFuncSetAttribute(salp_step_kernel_pipe4, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)pipe4_smem_bytes(widest, false)) != cudaSuccess)
+      const int bytes = (int)pipe4_smem_bytes(widest, false);
+      if (cudaFuncSetAttribute(salp_step_kernel_pipe4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess ||
+          cudaFuncSetAttribute(salp_step_kernel_pipe4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess)
         return SALP_ERR_CUDA;
       if (dev >= 0 && dev < 64) configured4[dev] = true;
     }
-    salp_step_kernel_pipe4<<<grid_for(v.n, 32), SALP_P4_THREADS, pipe4_smem_bytes(p, dv.axisym != 0), stream>>>(
-        p, dv, v, io, flags, order);
+    if (flags & SALP_STEP_CHECK_HANDOFF)      // (a separate kernel: the production one keeps its register allocation)
+      salp_step_kernel_pipe4<true><<<grid_for(v.n, 32), SALP_P4_THREADS, pipe4_smem_bytes(p, dv.axisym != 0), stream>>>(
+          p, dv, v, io, flags, order);
+    else
+      salp_step_kernel_pipe4<false><<<grid_for(v.n, 32), SALP_P4_THREADS, pipe4_smem_bytes(p, dv.axisym != 0), stream>>>(
+          p, dv, v, io, flags, order);
     name = "salp_step_kernel_pipe4";
     SALP_LAUNCH_CHECK();
     return launches + 1;

@@ -57,7 +57,8 @@ struct P4Layout {
   static constexpr size_t ring3a = ring1 + sizeof(float4) * SALP_P4_SLOTS1 * 2 * 32;           // [SLOTS3][32] float4 (v0 v1 v2 w0)
   static constexpr size_t ring3b = ring3a + sizeof(float4) * SALP_P4_SLOTS3 * 32;              // [SLOTS3][32] float2 (w1 w2)
   static constexpr size_t merge = ring3b + sizeof(float2) * SALP_P4_SLOTS3 * 32;               // [MERGE][32] double
-  static constexpr size_t tile = merge + sizeof(double) * SALP_P4_MERGE * 32;                  // [2][32][D] float
+  static constexpr size_t tags = merge + sizeof(double) * SALP_P4_MERGE * 32;                  // [SLOTS1 + SLOTS2 + SLOTS3][32] int (checked mode)
+  static constexpr size_t tile = tags + sizeof(int) * (SALP_P4_SLOTS1 + SALP_P4_SLOTS2 + SALP_P4_SLOTS3) * 32;   // [2][32][D] float
 };
 static inline size_t pipe4_smem_bytes(const SalpParams& p, bool axi) {
   const size_t tile = sizeof(float) * 2 * 32 * (SALP_OBS_BASE + 2 * p.num_obstacles);
@@ -98,7 +99,12 @@ __device__ __forceinline__ void p4_run_chunk(int j0, int je, int K, int& dn, Ite
   }
 }
 
-template <bool AXI>
+// CHECK (SALP_STEP_CHECK_HANDOFF): every ring row carries the substep index it was written for, in a
+// separate tag plane; the consumer compares it with the substep it is about to use and raises
+// SALP_ERR_HANDOFF otherwise.  A row read before its producer wrote it, or overwritten before its
+// consumer read it, shows up as a wrong tag.  (compute-sanitizer is closed on the measurement pool;
+// this is the repo's own race evidence, tests/test_gpu_parity.py.)
+template <bool AXI, bool CHECK>
 __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpDerived& dv, const SalpView& v,
                                                 const SalpStepIO& io, uint32_t flags, const int32_t* __restrict__ order,
                                                 unsigned char* smem) {
@@ -110,6 +116,9 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
   float4* ring3a = reinterpret_cast<float4*>(smem + L::ring3a);
   float2* ring3b = reinterpret_cast<float2*>(smem + L::ring3b);
   double* merge = reinterpret_cast<double*>(smem + L::merge);
+  int* tags1 = reinterpret_cast<int*>(smem + L::tags);
+  int* tags2 = tags1 + SALP_P4_SLOTS1 * 32;
+  int* tags3 = tags2 + SALP_P4_SLOTS2 * 32;
   float* tile = reinterpret_cast<float*>(smem + L::tile);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t tid = (int64_t)blockIdx.x * 32 + lane;
@@ -144,6 +153,10 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
   // ring rows of substep j (planes of quads)
   auto row1 = [&](int j) { return ring1 + (j % SALP_P4_SLOTS1) * 2 * 32 + lane; };
   auto row2 = [&](int j) { return ring2 + (j % SALP_P4_SLOTS2) * Q2 * 32 + lane; };
+  auto put_tag = [&](int* plane, int slots, int j) { if (CHECK) plane[(j % slots) * 32 + lane] = j; };
+  auto check_tag = [&](const int* plane, int slots, int j) {
+    if (CHECK && plane[(j % slots) * 32 + lane] != j) raise_status(v, SALP_ERR_HANDOFF);
+  };
 
   if (warp == 3) {
     // ---------------- front: fp64 shape chain + backward differences, j = 1..kA ----------------
@@ -170,9 +183,12 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
             shape_front(p, dv, cx.plan, tj1, j + 1, pp.k_T0, pp.k_jet, st, f1);
             front_store(f0, row1(j));
             front_store(f1, row1(j + 1));
+            put_tag(tags1, SALP_P4_SLOTS1, j);
+            put_tag(tags1, SALP_P4_SLOTS1, j + 1);
           } else if (j <= kA) {
             shape_front(p, dv, cx.plan, tj, j, pp.k_T0, pp.k_jet, st, f0);
             front_store(f0, row1(j));
+            put_tag(tags1, SALP_P4_SLOTS1, j);
           }
           tj = rn::dadd(tj1, p.dt);
           j += 2;
@@ -180,6 +196,7 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
           if (j <= kA) {
             shape_front(p, dv, cx.plan, tj, j, pp.k_T0, pp.k_jet, st, f0);
             front_store(f0, row1(j));
+            put_tag(tags1, SALP_P4_SLOTS1, j);
           }
           tj = tj1;
           j += 1;
@@ -201,8 +218,10 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
       ShapeFront f;
       Coef32 g;
       front_load(f, row1(j));
+      check_tag(tags1, SALP_P4_SLOTS1, j);
       make_coefs_R<AXI>(dv, dir, f, g);
       coef_store_R<AXI>(g, row2(j));
+      put_tag(tags2, SALP_P4_SLOTS2, j);
     };
     int j = 1;
     for (int c = 0; c < nch2; c++) {
@@ -241,6 +260,7 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
     auto kin_iter = [&](int j, bool at32) {
       const float4 a = ring3a[(j % SALP_P4_SLOTS3) * 32 + lane];
       const float2 bb = ring3b[(j % SALP_P4_SLOTS3) * 32 + lane];
+      check_tag(tags3, SALP_P4_SLOTS3, j);
       kin_world(dv, s);
       if (at32) flush_world(b, s);
       s.v0 = a.x; s.v1 = a.y; s.v2 = a.z; s.w0 = a.w; s.w1 = bb.x; s.w2 = bb.y;
@@ -276,11 +296,14 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
       ShapeFront f;
       front_load(f, row1(j));
       coef_load_R<AXI>(g, row2(j));
+      check_tag(tags1, SALP_P4_SLOTS1, j);
+      check_tag(tags2, SALP_P4_SLOTS2, j);
       make_coefs_T<AXI>(dv, dir, f, g);
     };
     auto hand_over = [&](int j) {
       ring3a[(j % SALP_P4_SLOTS3) * 32 + lane] = make_float4(s.v0, s.v1, s.v2, s.w0);
       ring3b[(j % SALP_P4_SLOTS3) * 32 + lane] = make_float2(s.w1, s.w2);
+      put_tag(tags3, SALP_P4_SLOTS3, j);
     };
     // iteration j: body-frame integrals of step j - 1, dynamics of substep j, (v, w) of step j to the ring
     auto dyn_iter_load = [&](int j, bool at32) {         // the shape is moving
@@ -377,12 +400,13 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
   }
 }
 
+template <bool CHECK>
 __global__ void __launch_bounds__(SALP_P4_THREADS, 1)
 salp_step_kernel_pipe4(const __grid_constant__ SalpParams p, const __grid_constant__ SalpDerived dv,
                        const __grid_constant__ SalpView v, const __grid_constant__ SalpStepIO io, uint32_t flags,
                        const int32_t* __restrict__ order) {
   extern __shared__ __align__(16) unsigned char pipe4_smem[];
   // (block-uniform: dv is a kernel argument; both forms give the same bits for axisymmetric parameters)
-  if (dv.axisym) salp_pipe4_body<true>(p, dv, v, io, flags, order, pipe4_smem);
-  else salp_pipe4_body<false>(p, dv, v, io, flags, order, pipe4_smem);
+  if (dv.axisym) salp_pipe4_body<true, CHECK>(p, dv, v, io, flags, order, pipe4_smem);
+  else salp_pipe4_body<false, CHECK>(p, dv, v, io, flags, order, pipe4_smem);
 }

@@ -21,6 +21,12 @@ from . import spaces
 from .batch import SalpBatch
 from .params import EPISODE_METRIC_NAMES, REWARD_TERM_NAMES, SalpParams, default_params
 
+try:  # pragma: no cover - gymnasium is not in the build image
+    import gymnasium as _gym
+    _EnvBase = _gym.Env
+except Exception:
+    _EnvBase = object
+
 
 class Nozzle:
     """Constructor-compatible with reference Nozzle (src/robot.py:20-47)."""
@@ -107,8 +113,10 @@ def params_from_robot(robot: Robot | None, *, width=900, height=700, num_obstacl
     return p
 
 
-class SalpRobotEnv:
-    """Single-env gymnasium surface (reference src/salp_robot_env.py:22-299), one GPU env."""
+class SalpRobotEnv(_EnvBase):
+    """Single-env gymnasium surface (reference src/salp_robot_env.py:22-299), one GPU env.
+    A `gymnasium.Env` subclass wherever gymnasium is importable (so `check_env`, `Monitor` and
+    `make_vec_env` accept it); a plain class with the same methods otherwise."""
 
     metadata = {"render_modes": ["human", "rgb_array"], "render_fps": 60}
 
@@ -136,6 +144,7 @@ class SalpRobotEnv:
         self.action = np.zeros(3)
         self.record = bool(record)         # Robot.enable_history_recording(): per-substep histories in `info`
         self.last_history = None
+        self.reset()                       # the reference resets in its constructor (salp_robot_env.py:112)
 
     def enable_history_recording(self):
         self.record = True
@@ -145,6 +154,8 @@ class SalpRobotEnv:
 
     # ---- gymnasium API ----
     def reset(self, seed=None, options=None):
+        if _EnvBase is not object:
+            super().reset(seed=seed)       # gymnasium bookkeeping (np_random); the reference never uses it either
         if seed is not None:
             self.action_space.seed(seed)
         obs = self._batch.reset()

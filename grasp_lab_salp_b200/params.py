@@ -24,6 +24,7 @@ STEP_SORT_BY_K = 2
 STEP_PIPELINE = 4
 STEP_FUSED = 8
 STEP_GENERIC = 16
+STEP_CHECK_HANDOFF = 32
 
 RAND_ACTION, RAND_OBSERVATION, RAND_DYNAMICS, RAND_DISTURBANCE, RAND_LATENCY = 1, 2, 4, 8, 16
 

@@ -56,6 +56,7 @@ class _VecEnvSurface:
         if info_mode not in ("full", "lazy", "auto"):
             raise ValueError("info_mode must be 'full', 'lazy' or 'auto'")
         self._full_infos = info_mode == "full" or (info_mode == "auto" and self.num_envs <= 64)
+        self._attrs: dict = {}        # attributes set through set_attr(): name -> {env index: value}
 
     # ---- VecEnv API ----
     def reset(self):
@@ -124,27 +125,72 @@ class _VecEnvSurface:
             return [indices]
         return indices
 
+    _STATE_ATTRS = ("target_point", "obstacles")
+
     def get_attr(self, attr_name: str, indices=None):
         idx = list(self._indices(indices))
+        if attr_name in self._attrs:
+            own = self._attrs[attr_name]
+            if all(i in own for i in idx):
+                return [own[i] for i in idx]
         if attr_name == "render_mode":
             return [None for _ in idx]
-        if attr_name in ("target_point",):
+        if attr_name == "target_point":
             tx, ty = self.batch.get_state("target_x"), self.batch.get_state("target_y")
             return [np.array([tx[i], ty[i]], np.float32) for i in idx]
         if attr_name == "obstacles":
             cols = [(self.batch.get_state(f"obstacle{k}_x"), self.batch.get_state(f"obstacle{k}_y"))
                     for k in range(self.params.num_obstacles)]
             return [[np.array([cx[i], cy[i]], np.float32) for cx, cy in cols] for i in idx]
+        if attr_name in self._attrs:
+            own = self._attrs[attr_name]
+            return [own.get(i) for i in idx]
         if hasattr(self, attr_name):
             v = getattr(self, attr_name)
             return [v for _ in idx]
         raise AttributeError(attr_name)
 
     def set_attr(self, attr_name: str, value: Any, indices=None):
-        raise AttributeError(f"SalpCudaVecEnv: attribute {attr_name!r} cannot be set per env; "
-                             "use batch.set_state(column, values) for simulator state")
+        """SB3 semantics: set `attr_name` of the selected envs.  `target_point` / `obstacles` write the
+        simulator's scene columns (what the reference's attributes of that name hold); any other name
+        is kept per env and handed back by get_attr()."""
+        idx = list(self._indices(indices))
+        if attr_name == "target_point":
+            t = np.asarray(value, np.float32).reshape(2)
+            for a, col in zip(t, ("target_x", "target_y")):
+                v = self.batch.get_state(col)
+                v[idx] = a
+                self.batch.set_state(col, v)
+            return
+        if attr_name == "obstacles":
+            o = np.asarray(value, np.float32).reshape(self.params.num_obstacles, 2)
+            for k in range(self.params.num_obstacles):
+                for a, ax in zip(o[k], "xy"):
+                    v = self.batch.get_state(f"obstacle{k}_{ax}")
+                    v[idx] = a
+                    self.batch.set_state(f"obstacle{k}_{ax}", v)
+            return
+        own = self._attrs.setdefault(attr_name, {})
+        for i in idx:
+            own[i] = value
 
     def env_method(self, method_name: str, *args, indices=None, **kwargs):
+        """SB3 semantics: call a method of the selected envs, one result per env.  The envs are rows of
+        one batch, so only the reference env's state-free or reset-like methods exist."""
+        idx = list(self._indices(indices))
+        if method_name == "reset":
+            mask = np.zeros(self.num_envs, np.uint8)
+            mask[idx] = 1
+            obs = self.batch.reset(mask)
+            return [(obs[i].copy(), {}) for i in idx]
+        if method_name in ("render", "close", "enable_action_randomization", "enable_observation_randomization",
+                           "enable_latency"):
+            if method_name.startswith("enable_"):
+                raise AttributeError(f"{method_name}: robustness switches are construction-time parameters here "
+                                     "(SalpParams.randomization), not per-env calls")
+            return [None for _ in idx]
+        if method_name == "get_wrapper_attr":
+            return self.get_attr(args[0], indices)
         raise AttributeError(f"SalpCudaVecEnv has no per-env method {method_name!r} (envs are rows of one batch)")
 
     def env_is_wrapped(self, wrapper_class, indices=None):

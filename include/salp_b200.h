@@ -45,7 +45,8 @@ typedef enum SalpStatus {
   SALP_ERR_CUDA = -2,         /* CUDA runtime failure (message in salp_last_error) */
   SALP_ERR_NO_DEVICE = -3,    /* no usable sm_100 GPU: there is NO CPU fallback */
   SALP_ERR_RANGE = -4,        /* an action drove the cycle past SALP_MAX_SUBSTEPS */
-  SALP_ERR_ALLOC = -5
+  SALP_ERR_ALLOC = -5,
+  SALP_ERR_HANDOFF = -6       /* SALP_STEP_CHECK_HANDOFF: a pipeline-kernel warp read a ring row that was not the one written for it */
 } SalpStatus;
 
 /* Arithmetic the substep loop runs in. */
@@ -74,6 +75,10 @@ typedef enum SalpPrecision {
 /* The loop has a form for axisymmetric coefficient sets (axes 1 and 2 alike, as in the defaults) that
  * shares their entries; it is chosen automatically and gives the same bits as the general form. */
 #define SALP_STEP_GENERIC 16u      /* force the general form (tests) */
+/* Checked hand-off (tests): the pipeline kernel tags every shared-memory ring row with the substep it
+ * was written for and verifies the tag on the consuming warp; a mismatch sets SALP_ERR_HANDOFF in the
+ * sticky status (salp_check).  Same results, a few per cent slower. */
+#define SALP_STEP_CHECK_HANDOFF 32u
 
 /*
  * Every literal the reference hard-codes on this path, as one POD.

@@ -1,6 +1,8 @@
 """The reference-facing surfaces: gymnasium-style SalpRobotEnv and the SB3-VecEnv-shaped
 SalpCudaVecEnv.  CPU variants run on the host build of the kernel body (tests/emu); the GPU
 variants (marked gpu) run the same checks on the CUDA library."""
+import os
+
 import numpy as np
 import pytest
 
@@ -155,3 +157,137 @@ def test_history_feed_emu():
 @pytest.mark.gpu
 def test_history_feed_gpu():
     _history_feed(_cdll(True))
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference's own consumer of `info`: DetailedMetricsCallback (src/tensorboard_callback.py)
+# ---------------------------------------------------------------------------------------------
+def _load_reference_callback():
+    """The UNMODIFIED DetailedMetricsCallback, imported from the reference sources with a dummy
+    `stable_baselines3.common.callbacks.BaseCallback` (SB3 is not installed in this image)."""
+    import importlib.util
+    import sys
+    import types
+    from oracle import ref_harness
+    d = ref_harness.reference_dir()
+    path = None if d is None else os.path.join(d, "tensorboard_callback.py")
+    if path is None or not os.path.isfile(path):
+        pytest.skip("reference tensorboard_callback.py not available (tools/stage_reference.py)")
+
+    class BaseCallback:               # the part of SB3's BaseCallback that the reference callback touches
+        def __init__(self, verbose=0):
+            self.verbose = verbose
+            self.n_calls = 0
+            self.locals = {}
+            self.records = {}
+            self.logger = types.SimpleNamespace(record=lambda k, v: self.records.__setitem__(k, v))
+
+        def on_step(self):
+            self.n_calls += 1
+            return self._on_step()
+
+    names = ["stable_baselines3", "stable_baselines3.common", "stable_baselines3.common.callbacks"]
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        for k in names:
+            sys.modules[k] = types.ModuleType(k)
+        sys.modules[names[2]].BaseCallback = BaseCallback
+        spec = importlib.util.spec_from_file_location("salp_ref_tensorboard_callback", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod.DetailedMetricsCallback
+
+
+def _reference_callback_reads_what_the_reference_env_would_give(cdll, rel):
+    """Drives SalpCudaVecEnv with the actions and scenes of a golden trace of the live reference and
+    feeds every step's (infos, dones) to the reference's DetailedMetricsCallback._on_step; what the
+    callback collected must be what the reference's own env + SB3 Monitor would have handed it
+    (recomputed here from the golden file): Monitor r / l, success / truncation, and the nine
+    navigation / action / velocity metrics of salp_robot_env.py:399-447.  The callback's
+    reward-component deques stay empty, as they do with the reference: it looks for `avg_r_track`
+    while the env emits `avg_rewards_track` (tensorboard_callback.py:114-123 vs salp_robot_env.py:441-445)."""
+    Callback = _load_reference_callback()
+    g = load_golden("ref_random.npz")
+    acts = g["actions"]
+    n, T, _ = acts.shape
+    venv = SalpCudaVecEnv(n, golden_params(g, precision=PRECISION_F64), seed=0, info_mode="lazy", _cdll=cdll)
+    venv.batch.set_scene_pool(g["targets"], g["obstacles"])
+    venv.reset()
+    cb = Callback(log_freq=T)
+    keys = [str(k) for k in g["metric_keys"]]
+    want = {k: [] for k in ("r", "l", "success", "truncated", "path_length", "direct_distance", "path_efficiency",
+                            "final_distance", "initial_distance", "avg_compression", "avg_coast_time",
+                            "avg_nozzle_angle", "avg_velocity")}
+    ret = np.zeros(n)
+    length = np.zeros(n, int)
+    for t in range(T):
+        obs, rew, dones, infos = venv.step(acts[:, t])
+        cb.locals = {"infos": infos, "dones": dones}
+        assert cb.on_step() is True
+        ret += g["reward"][:, t]
+        length += 1
+        ended = (g["terminated"][:, t] | g["truncated"][:, t]).astype(bool)
+        np.testing.assert_array_equal(dones, ended)
+        for i in np.flatnonzero(ended):
+            want["r"].append(ret[i])
+            want["l"].append(length[i])
+            tl_trunc = bool(g["truncated"][i, t]) and not bool(g["terminated"][i, t])      # SB3's TimeLimit.truncated
+            want["success"].append(0.0 if tl_trunc else 1.0)
+            want["truncated"].append(1.0 if tl_trunc else 0.0)
+            for k in list(want)[4:]:
+                want[k].append(g["metrics"][i, t, keys.index(k)])
+            ret[i] = 0.0
+            length[i] = 0
+    assert len(want["r"]) >= 20            # the trace does end episodes
+    got = {"r": cb.episode_rewards, "l": cb.episode_lengths, "success": cb.episode_successes,
+           "truncated": cb.episode_truncations, "path_length": cb.episode_path_lengths,
+           "direct_distance": cb.episode_direct_distances, "path_efficiency": cb.episode_efficiencies,
+           "final_distance": cb.episode_final_distances, "initial_distance": cb.episode_initial_distances,
+           "avg_compression": cb.episode_compressions, "avg_coast_time": cb.episode_coast_times,
+           "avg_nozzle_angle": cb.episode_nozzle_angles, "avg_velocity": cb.episode_velocities}
+    for k, w in want.items():
+        # (the reference averages its float32 action lists in float32, salp_robot_env.py:420-427)
+        tol = 1e-6 if k in ("avg_compression", "avg_coast_time", "avg_nozzle_angle") else rel
+        np.testing.assert_allclose(np.array(list(got[k]), float), np.array(w, float), rtol=tol, atol=tol, err_msg=k)
+    assert len(cb.episode_r_tracks) == 0 and len(cb.episode_r_smooths) == 0
+    # the aggregated TensorBoard scalars are logged from those deques (log_freq = T)
+    assert cb.records["custom/navigation/success_rate"] == pytest.approx(np.mean(want["success"]))
+    assert cb.records["custom/path/efficiency"] == pytest.approx(np.mean(want["path_efficiency"]), rel=rel)
+    assert cb.records["reward/stats/total_mean"] == pytest.approx(np.mean(want["r"]), rel=rel)
+    venv.close()
+
+
+def test_reference_metrics_callback_on_the_vec_env_cpu():
+    _reference_callback_reads_what_the_reference_env_would_give(_cdll(False), 1e-8)
+
+
+@pytest.mark.gpu
+def test_reference_metrics_callback_on_the_vec_env_gpu():
+    _reference_callback_reads_what_the_reference_env_would_give(_cdll(True), 1e-8)
+
+
+def _set_attr_and_env_method(cdll):
+    venv = SalpCudaVecEnv(6, seed=1, info_mode="lazy", _cdll=cdll)
+    venv.reset()
+    venv.set_attr("target_point", np.array([1.25, -0.5], np.float32), indices=[1, 4])
+    tp = venv.get_attr("target_point")
+    np.testing.assert_array_equal(tp[1], [1.25, -0.5])
+    np.testing.assert_array_equal(tp[4], [1.25, -0.5])
+    assert not np.array_equal(tp[0], tp[1])
+    venv.set_attr("my_tag", "x", indices=2)
+    assert venv.get_attr("my_tag", indices=[2, 3]) == ["x", None]
+    out = venv.env_method("reset", indices=[0, 5])
+    assert len(out) == 2 and out[0][0].shape == (10,) and out[0][1] == {}
+    with pytest.raises(AttributeError):
+        venv.env_method("no_such_method")
+    venv.close()
+
+
+def test_set_attr_and_env_method_cpu():
+    _set_attr_and_env_method(_cdll(False))

@@ -384,3 +384,31 @@ def test_other_obstacle_count_and_masked_device_reset():
     np.testing.assert_allclose(obs_d.cpu().numpy()[mask == 1], obs_o[mask == 1], rtol=1e-6, atol=1e-6)
     np.testing.assert_array_equal(prod.get_state("episode_index"), orc.get_state("episode_index"))
     np.testing.assert_array_equal(prod.get_state("cycle"), orc.get_state("cycle"))
+
+
+def test_pipeline_handoff_tags_at_full_size():
+    """SALP_STEP_CHECK_HANDOFF: every shared-memory ring row of the warp-specialised kernel carries the
+    substep index it was produced for and each consuming warp verifies it (salp_pipe4_kernel.cuh).
+    BASELINE's 4096 envs (one block on almost every SM, all four warps busy), 60 free-running steps
+    with auto-reset, plus ragged / K = 0 / short-cycle batches: no wrong tag, and the checked kernel
+    gives the same bits as the unchecked one.  (compute-sanitizer's racecheck is closed on the
+    measurement pool: `compute-sanitizer is closed on this pool and stays closed`.)"""
+    from grasp_lab_salp_b200.params import FIELDS
+    g = load_golden("ref_random.npz")
+    for n, T in ((4096, 60), (1000, 12), (77, 12)):
+        acts = uniform_actions(np.random.default_rng(31), T, n)
+        acts[1, : min(n, 64)] = 0.0                       # K = 0 warps
+        acts[2, :, 1] *= 0.02                             # short cycles: the shape moves almost all the time
+        a, b = SalpBatch(n, golden_params(g), seed=5), SalpBatch(n, golden_params(g), seed=5)
+        np.testing.assert_array_equal(a.reset(), b.reset())
+        for t in range(T):
+            ra = a.step(acts[t], auto_reset=True, check_handoff=True)
+            rb = b.step(acts[t], auto_reset=True)
+            assert a.last_step_kernel == "salp_step_kernel_pipe4"
+            for x, y in zip(ra, rb):
+                np.testing.assert_array_equal(x, y)
+        a.check()                                         # raises SALP_ERR_HANDOFF on a wrong tag
+        for col in FIELDS:
+            np.testing.assert_array_equal(a.get_state(col), b.get_state(col), err_msg=col)
+        a.close()
+        b.close()

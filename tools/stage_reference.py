@@ -3,7 +3,8 @@
 
 `gpurun` ships only /root/repo; /root/reference does not exist there.  BASELINE.md section 3 /
 SURVEY section 7 step 0 reserve the git-ignored `baseline/_ref/` for the reference: this script copies
-the four hot-path files byte for byte into baseline/_ref/src/ and writes their sha256 next to them
+the four hot-path files (and the metrics callback that consumes their `info`, for the
+conformance test) byte for byte into baseline/_ref/src/ and writes their sha256 next to them
 (bench.py prints the hashes of what it timed).  Nothing under baseline/_ref is tracked by git or
 imported by the product; oracle/ref_harness.py finds it ($SALP_REF_DIR, then baseline/_ref/src, then
 /root/reference/src).
@@ -19,7 +20,7 @@ import shutil
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-FILES = ("dynamics.py", "geometry.py", "robot.py", "salp_robot_env.py")
+FILES = ("dynamics.py", "geometry.py", "robot.py", "salp_robot_env.py", "tensorboard_callback.py")
 
 
 def stage(src="/root/reference/src", quiet=False):
