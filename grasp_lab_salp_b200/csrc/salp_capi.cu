@@ -9,6 +9,9 @@
 
 #include "salp_common.cuh"
 
+#define SALP_HOST_RANGES 8           // salp_step_host, K-sorted: env ranges whose D2H overlaps the next range's kernel
+#define SALP_HOST_RANGE_MIN 65536    // ... each at least this many envs (the K-sort balances warps WITHIN a range)
+
 struct SalpSim {
   SalpParams params;
   SalpView view;
@@ -32,6 +35,11 @@ struct SalpSim {
   float* d_pool_targets;
   float* d_pool_obstacles;
   cudaStream_t host_stream;
+  // chunked host step (K-sorted, large batches): copy streams and per-range events
+  cudaStream_t h2d_stream, d2h_stream, step_stream2;
+  SalpScratch scratch2;        // K-sort scratch of the second compute stream
+  cudaEvent_t ev_in[SALP_HOST_RANGES], ev_done[SALP_HOST_RANGES];
+  bool chunk_ready;
 };
 
 static thread_local std::string g_create_error;
@@ -165,6 +173,13 @@ int salp_destroy(salp_handle h) {
                   h->d_mask, h->d_pool_targets, h->d_pool_obstacles};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->host_stream) cudaStreamDestroy(h->host_stream);
+  if (h->chunk_ready) {
+    cudaStreamDestroy(h->h2d_stream);
+    cudaStreamDestroy(h->d2h_stream);
+    cudaStreamDestroy(h->step_stream2);
+    cudaFree(h->scratch2.K); cudaFree(h->scratch2.order); cudaFree(h->scratch2.hist);
+    for (int r = 0; r < SALP_HOST_RANGES; r++) { cudaEventDestroy(h->ev_in[r]); cudaEventDestroy(h->ev_done[r]); }
+  }
   delete h;
   return SALP_OK;
 }
@@ -205,6 +220,7 @@ int salp_create(const SalpParams* params, int64_t num_envs, int device, uint64_t
   h->d_substeps = nullptr;
   h->d_pool_targets = h->d_pool_obstacles = nullptr;
   h->host_stream = nullptr;
+  h->chunk_ready = false;
   h->params = *params;
   h->device = device;
   h->obs_dim = SALP_OBS_BASE + 2 * params->num_obstacles;
@@ -332,6 +348,103 @@ static bool zero_copy_enabled() {
 //  * staged (pageable caller buffers, K-sorted steps, F64): H2D of the actions, kernel on the
 //    handle's own device buffers, one D2H per output.
 // The optional extras (reward_terms, substeps, episode_metrics) are always staged.
+static bool page_locked(const void* p) {
+  cudaPointerAttributes at;
+  if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
+// K-sorted host step of a large batch in contiguous env RANGES: each range is planned, K-sorted and
+// stepped on its own (sub-view of the state, global env ids kept), and as soon as a range's kernel is
+// done its slices of obs / reward / flags / terminal obs go back over PCIe on a second stream while
+// the next range integrates; the action slices are uploaded ahead on a third.  Same results as the
+// one-launch step (per-env results do not depend on which envs share a warp).  Needs page-locked
+// caller buffers (asynchronous copies); otherwise the plain staged path below is used.
+static int step_host_ranges(SalpSim* h, const SalpStepIO* io, uint32_t flags, int ranges) {
+  const int64_t n = h->view.n;
+  const int D = h->obs_dim;
+  cudaStream_t s = h->host_stream;
+  if (!h->chunk_ready) {
+    CU(h, cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+    CU(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    CU(h, cudaStreamCreateWithFlags(&h->step_stream2, cudaStreamNonBlocking));
+    CU(h, cudaMalloc((void**)&h->scratch2.K, sizeof(int32_t) * n));
+    CU(h, cudaMalloc((void**)&h->scratch2.order, sizeof(int32_t) * n));
+    CU(h, cudaMalloc((void**)&h->scratch2.hist, sizeof(int32_t) * SALP_SORT_BINS));
+    for (int r = 0; r < SALP_HOST_RANGES; r++) {
+      CU(h, cudaEventCreateWithFlags(&h->ev_in[r], cudaEventDisableTiming));
+      CU(h, cudaEventCreateWithFlags(&h->ev_done[r], cudaEventDisableTiming));
+    }
+    h->chunk_ready = true;
+  }
+  const int64_t per = ((n + ranges - 1) / ranges + 31) / 32 * 32;
+  for (int r = 0; r < ranges; r++) {
+    const int64_t first = (int64_t)r * per;
+    if (first >= n) break;
+    const int64_t cnt = n - first < per ? n - first : per;
+    CU(h, cudaMemcpyAsync(h->d_actions + 3 * first, io->actions + 3 * first, sizeof(float) * 3 * cnt,
+                          cudaMemcpyHostToDevice, h->h2d_stream));
+    CU(h, cudaEventRecord(h->ev_in[r], h->h2d_stream));
+  }
+  for (int r = 0; r < ranges; r++) {
+    const int64_t first = (int64_t)r * per;
+    if (first >= n) break;
+    const int64_t cnt = n - first < per ? n - first : per;
+    SalpView v = h->view;
+#if SALP_STATE_AOS
+    v.f64 += first * SALP_NUM_F64_FIELDS;
+    v.f32 += first * SALP_NUM_F32;
+    v.i32 += first * SALP_NUM_I32;
+#else
+#error "step_host_ranges needs the record-per-env state layout"
+#endif
+    v.n = cnt;
+    v.env_id_offset += first;
+    if (v.pool_P > 0) {
+      v.pool_targets += first * v.pool_P * 2;
+      v.pool_obstacles += first * v.pool_P * h->params.num_obstacles * 2;
+    }
+    SalpStepIO d;
+    d.actions = h->d_actions + 3 * first;
+    d.obs = h->d_obs + D * first;
+    d.reward = h->d_reward + first;
+    d.terminated = h->d_terminated + first;
+    d.truncated = h->d_truncated + first;
+    d.terminal_obs = io->terminal_obs ? h->d_terminal_obs + D * first : nullptr;
+    d.reward_terms = io->reward_terms ? h->d_terms + SALP_NUM_REWARD_TERMS * first : nullptr;
+    d.substeps = io->substeps ? h->d_substeps + first : nullptr;
+    d.episode_metrics = io->episode_metrics ? h->d_metrics + SALP_NUM_EPISODE_METRICS * first : nullptr;
+    // two compute streams, alternating: the thin tail of one range's kernel (its longest warps)
+    // overlaps the head of the next range's
+    cudaStream_t cs = (r & 1) ? h->step_stream2 : s;
+    CU(h, cudaStreamWaitEvent(cs, h->ev_in[r], 0));
+    int rc = salp_launch_step(h->params, v, d, flags, (r & 1) ? h->scratch2 : h->scratch, cs, &h->last_kernel);
+    if (rc < 0) return cuda_fail(h, cudaGetLastError(), "salp_step_host launch (range)");
+    h->launches += rc;
+    CU(h, cudaEventRecord(h->ev_done[r], cs));
+    cudaStream_t c = h->d2h_stream;
+    CU(h, cudaStreamWaitEvent(c, h->ev_done[r], 0));
+    CU(h, cudaMemcpyAsync(io->obs + D * first, d.obs, sizeof(float) * D * cnt, cudaMemcpyDeviceToHost, c));
+    CU(h, cudaMemcpyAsync(io->reward + first, d.reward, sizeof(float) * cnt, cudaMemcpyDeviceToHost, c));
+    CU(h, cudaMemcpyAsync(io->terminated + first, d.terminated, cnt, cudaMemcpyDeviceToHost, c));
+    CU(h, cudaMemcpyAsync(io->truncated + first, d.truncated, cnt, cudaMemcpyDeviceToHost, c));
+    if (io->terminal_obs)
+      CU(h, cudaMemcpyAsync(io->terminal_obs + D * first, d.terminal_obs, sizeof(float) * D * cnt, cudaMemcpyDeviceToHost, c));
+    if (io->reward_terms)
+      CU(h, cudaMemcpyAsync(io->reward_terms + SALP_NUM_REWARD_TERMS * first, d.reward_terms,
+                            sizeof(double) * SALP_NUM_REWARD_TERMS * cnt, cudaMemcpyDeviceToHost, c));
+    if (io->substeps)
+      CU(h, cudaMemcpyAsync(io->substeps + first, d.substeps, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, c));
+    if (io->episode_metrics)
+      CU(h, cudaMemcpyAsync(io->episode_metrics + SALP_NUM_EPISODE_METRICS * first, d.episode_metrics,
+                            sizeof(double) * SALP_NUM_EPISODE_METRICS * cnt, cudaMemcpyDeviceToHost, c));
+  }
+  CU(h, cudaStreamSynchronize(h->d2h_stream));     // (waits for every range's kernel through the events)
+  CU(h, cudaStreamSynchronize(s));
+  CU(h, cudaStreamSynchronize(h->step_stream2));
+  return SALP_OK;
+}
+
 int salp_step_host(salp_handle h, const SalpStepIO* io, uint32_t flags) {
   if (!h || !io) return SALP_ERR_INVALID;
   if (!io->actions || !io->obs || !io->reward || !io->terminated || !io->truncated)
@@ -340,6 +453,12 @@ int salp_step_host(salp_handle h, const SalpStepIO* io, uint32_t flags) {
   cudaStream_t s = h->host_stream;
   const int64_t n = h->view.n;
   const int D = h->obs_dim;
+  if ((flags & SALP_STEP_SORT_BY_K) && n >= 2 * (int64_t)SALP_HOST_RANGE_MIN && page_locked(io->obs) &&
+      page_locked(io->actions) && page_locked(io->reward) && page_locked(io->terminated) && page_locked(io->truncated)) {
+    int ranges = (int)(n / SALP_HOST_RANGE_MIN);
+    ranges = ranges > SALP_HOST_RANGES ? SALP_HOST_RANGES : ranges;
+    return step_host_ranges(h, io, flags, ranges);
+  }
   // (K-sorted steps visit the envs in scattered order: 40-byte rows make poor PCIe writes --
   //  measured 12.7 ms vs 8.2 ms staged at 1 M envs -- so they keep the staged transport)
   const bool zc_ok = zero_copy_enabled() && h->params.precision == SALP_PRECISION_MIXED &&

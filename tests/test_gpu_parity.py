@@ -412,3 +412,30 @@ def test_pipeline_handoff_tags_at_full_size():
             np.testing.assert_array_equal(a.get_state(col), b.get_state(col), err_msg=col)
         a.close()
         b.close()
+
+
+def test_chunked_host_step_equals_single_launch():
+    """salp_step_host, K-sorted, large batch with page-locked buffers: the batch is stepped in
+    contiguous env ranges whose result copies overlap the next range's kernel (salp_capi.cu,
+    step_host_ranges).  Same bits as the one-launch staged path (pageable buffers), including the
+    ragged last range, the built-in Philox scenes (global env ids) and auto-reset."""
+    n, T = 300_003, 3           # 2 ranges of 150 016 envs, the last one ragged
+    g = load_golden("ref_random.npz")
+    acts = uniform_actions(np.random.default_rng(18), T, n)
+    pinned = SalpBatch(n, golden_params(g), seed=3)
+    paged = SalpBatch(n, golden_params(g), seed=3)
+    for name in ("obs", "terminal_obs", "reward", "terminated", "truncated"):
+        setattr(paged, name, np.full_like(getattr(paged, name), 7))       # plain numpy: not page-locked
+    a_pinned = pinned.host_buffer((n, 3), np.float32)
+    np.testing.assert_array_equal(pinned.reset(), paged.reset())
+    for t in range(T):
+        a_pinned[:] = acts[t]
+        o, r, te, tr = pinned.step(a_pinned, auto_reset=True, sort_by_k=True)
+        o2, r2, te2, tr2 = paged.step(acts[t].copy(), auto_reset=True, sort_by_k=True)
+        for x, y in ((o, o2), (r, r2), (te, te2), (tr, tr2), (pinned.terminal_obs, paged.terminal_obs),
+                     (pinned.substeps, paged.substeps), (pinned.terms, paged.terms)):
+            np.testing.assert_array_equal(x, y)
+    np.testing.assert_array_equal(pinned.get_state("episode_index"), paged.get_state("episode_index"))
+    np.testing.assert_array_equal(pinned.get_state("posw_x"), paged.get_state("posw_x"))
+    pinned.check()
+    paged.check()
