@@ -142,6 +142,13 @@ class PPOConfig:
                                       # reference env returns finite but astronomically large rewards for cycles next
                                       # to its integrator's stability limit, which would destroy any
                                       # value function; set to 0 to disable
+    normalize_reward: bool = True     # learner-side reward scaling, stable-baselines3 VecNormalize(norm_reward=True)
+                                      # semantics: r / sqrt(running variance of the discounted return), clipped to
+                                      # +-10.  The env's rewards span +-500: un-normalised, the value loss starts at
+                                      # 1e5, the critic's gradient dominates the global gradient-norm clip (0.5) and
+                                      # the actor's clipped gradient falls below Adam's eps -- the LSTM actor then does
+                                      # not move for the first ~15 M env-steps (profiles/README.md, round 1 curve).
+                                      # Episode statistics are always reported on the RAW env reward.
     cuda_graphs: bool = False         # MLP PPO on CUDA: replay the whole rollout and each minibatch step as CUDA graphs
     seed: int = 0
     hidden: tuple = (64, 64)
@@ -196,13 +203,18 @@ class PPO:
         self._roll_graph = self._upd_graph = None
         self._roll_calls = self._upd_calls = 0
         self.gen = torch.Generator(device=self.device)
-        self.gen.manual_seed(self.cfg.seed + 1)
+        self._gen_seed = self.cfg.seed + 1          # (+ rank below: shards must not share their exploration noise)
+        self.gen.manual_seed(self._gen_seed)
         self.low = torch.tensor(self.cfg.action_low, device=self.device)
         self.high = torch.tensor(self.cfg.action_high, device=self.device)
         self.obs = env.reset_t()
         n = env.num_envs
         self._ep_ret = torch.zeros(n, device=self.device)
         self._ep_len = torch.zeros(n, device=self.device)
+        # running variance of the discounted return (VecNormalize): per-env return accumulator and
+        # (count, mean, M2) merged batch-wise on the device (no host round trip, CUDA-graph capturable)
+        self._disc_ret = torch.zeros(n, device=self.device, dtype=torch.float64)
+        self._ret_stats = torch.tensor([1e-4, 0.0, 1e-4], device=self.device, dtype=torch.float64)
         self.env_steps = 0
         self.iteration = 0
         self.dist_world = 1
@@ -212,7 +224,12 @@ class PPO:
                 self.dist_world = dist.get_world_size()
                 for p in self.policy.parameters():          # identical initial weights on every rank
                     dist.broadcast(p.data, src=0)
-                self.graph_update = False                   # (the NCCL all-reduce stays outside CUDA graphs)
+                self.gen.manual_seed(self._gen_seed + 7919 * dist.get_rank())
+                # the minibatch step is captured WITH its NCCL gradient all-reduce (NCCL collectives are
+                # capturable); SALP_PPO_GRAPH_ALLREDUCE=0 keeps the multi-GPU update eager
+                import os
+                if os.environ.get("SALP_PPO_GRAPH_ALLREDUCE", "1") == "0":
+                    self.graph_update = False
         except Exception:
             pass
 
@@ -223,7 +240,33 @@ class PPO:
                         logp=torch.empty((T, N), device=dev), val=torch.empty((T, N), device=dev),
                         rew=torch.empty((T, N), device=dev), done=torch.empty((T, N), dtype=torch.bool, device=dev),
                         adv=torch.empty((T, N), device=dev), ret=torch.empty((T, N), device=dev),
-                        ep=torch.zeros(4, dtype=torch.float64, device=dev), mean_reward=torch.zeros((), device=dev))
+                        ep=torch.zeros(4, dtype=torch.float64, device=dev), mean_reward=torch.zeros((), device=dev),
+                        raw_sum=torch.zeros((), device=dev))
+
+    def _learner_reward(self, raw, done, bootstrap):
+        """Reward as the learner sees it: optional VecNormalize-style scaling by the running standard
+        deviation of the discounted return (statistics updated in place, device only), the SB3
+        time-limit bootstrap gamma * V(terminal_observation) (`bootstrap`, already in the learner's
+        units), and the safety clip.  `raw` is the env's reward with non-finite entries zeroed."""
+        cfg = self.cfg
+        rew = raw
+        if cfg.reward_clip > 0:
+            rew = raw = raw.clamp(-cfg.reward_clip, cfg.reward_clip)
+        if cfg.normalize_reward:
+            self._disc_ret.mul_(cfg.gamma).add_(raw.double())
+            st = self._ret_stats                       # Chan et al. batch merge of (count, mean, M2)
+            nb = float(raw.numel())
+            mb = self._disc_ret.mean()
+            m2b = (self._disc_ret - mb).pow(2).sum()
+            tot = st[0] + nb
+            delta = mb - st[1]
+            new_mean = st[1] + delta * nb / tot
+            new_m2 = st[2] + m2b + delta * delta * st[0] * nb / tot
+            st.copy_(torch.stack([tot, new_mean, new_m2]))
+            std = (st[2] / st[0]).sqrt().clamp_min(1e-4).float()
+            rew = (raw / std).clamp(-10.0, 10.0)
+            self._disc_ret.mul_((~done).double())
+        return rew + bootstrap
 
     def _rollout_body(self):
         """T env-steps + GAE, everything in place on persistent device buffers (so that the whole
@@ -232,6 +275,7 @@ class PPO:
         cfg, env, T, rb = self.cfg, self.env, self.cfg.n_steps, self._rb
         ep = rb["ep"]            # [sum return, sum length, successes, episodes] of the episodes that ended
         ep.zero_()
+        rb["raw_sum"].zero_()
         for t in range(T):
             a, logp, v = self.policy.act(self.obs, self.gen)
             rb["obs"][t].copy_(self.obs); rb["act"][t].copy_(a); rb["logp"][t].copy_(logp); rb["val"][t].copy_(v)
@@ -239,13 +283,13 @@ class PPO:
             obs, rew, term, trunc, term_obs = env.step_t(clipped)
             done = term | trunc
             timeout = (trunc & ~term).float()
-            with torch.no_grad():                 # SB3: bootstrap truncated episodes with V(terminal_observation)
-                rew = rew + cfg.gamma * self.policy.value(term_obs) * timeout
-            rew = torch.nan_to_num(rew, nan=0.0, posinf=0.0, neginf=0.0)
+            raw = torch.nan_to_num(rew, nan=0.0, posinf=0.0, neginf=0.0)       # the env's own reward (Monitor's `r`)
             if cfg.reward_clip > 0:
-                rew = rew.clamp(-cfg.reward_clip, cfg.reward_clip)
-            rb["rew"][t].copy_(rew); rb["done"][t].copy_(done)
-            self._ep_ret += rew
+                raw = raw.clamp(-cfg.reward_clip, cfg.reward_clip)
+            with torch.no_grad():                 # SB3: bootstrap truncated episodes with V(terminal_observation)
+                rew = self._learner_reward(raw, done, cfg.gamma * self.policy.value(term_obs) * timeout)
+            rb["rew"][t].copy_(rew); rb["done"][t].copy_(done); rb["raw_sum"] += raw.sum()
+            self._ep_ret += raw
             self._ep_len += 1
             d = done.to(torch.float64)
             ep += torch.stack([(self._ep_ret.double() * d).sum(), (self._ep_len.double() * d).sum(),
@@ -258,7 +302,7 @@ class PPO:
             last_value = self.policy.value(self.obs)
         adv, ret = compute_gae(rb["rew"], rb["val"], rb["done"], last_value, cfg.gamma, cfg.gae_lambda)
         rb["adv"].copy_(adv); rb["ret"].copy_(ret)
-        rb["mean_reward"].copy_(rb["rew"].mean())
+        rb["mean_reward"].copy_(rb["raw_sum"] / float(T * env.num_envs))
 
     def collect(self):
         T, N = self.cfg.n_steps, self.env.num_envs
@@ -325,6 +369,13 @@ class PPO:
     def update(self, roll):
         cfg = self.cfg
         n, bs = self._update_domain(roll)
+        if self.dist_world > 1:       # every rank must issue the same number of gradient all-reduces: uneven
+            import torch.distributed as dist      # shards (envs % world != 0) use the smallest shard's count
+            t = torch.tensor([n], device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            n_common = int(t.item())
+        else:
+            n_common = n
         stats = getattr(self, "_upd_stats", None)
         if stats is None:
             stats = self._upd_stats = torch.zeros(4, device=self.device)
@@ -333,7 +384,7 @@ class PPO:
         count = 0
         for _ in range(cfg.n_epochs):
             perm = torch.randperm(n, device=self.device, generator=self.gen)
-            for s in range(0, n - bs + 1, bs):
+            for s in range(0, n_common - bs + 1, bs):
                 self._upd_idx.copy_(perm[s:s + bs])
                 self._upd_calls += 1
                 if self.graph_update and self._upd_calls > 3:
@@ -349,6 +400,26 @@ class PPO:
                 count += 1
         kl, clipf, vl, pl = (stats / max(count, 1)).tolist()
         return dict(approx_kl=kl, clip_fraction=clipf, value_loss=vl, policy_loss=pl)
+
+    def allreduce_seconds_per_step(self, reps: int = 50) -> float:
+        """Device time of ONE gradient all-reduce of this policy's size (CUDA events, after warm-up):
+        multiplied by the optimiser steps of an update it gives the all-reduce share of the update
+        (BASELINE.md section 4).  0.0 on one GPU."""
+        if self.dist_world == 1:
+            return 0.0
+        import torch.distributed as dist
+        n = sum(p.numel() for p in self.policy.parameters())
+        flat = torch.zeros(n, device=self.device)
+        for _ in range(5):
+            dist.all_reduce(flat)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            dist.all_reduce(flat)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps
 
     def _reduce_stat(self, total, count):
         if self.dist_world > 1:
@@ -451,6 +522,7 @@ class RecurrentPPO(PPO):
             dst.copy_(src)
         ep = rb["ep"]
         ep.zero_()
+        rb["raw_sum"].zero_()
         for t in range(T):
             with torch.no_grad():
                 mean, v, new_state = self.policy.step(self.obs, self.state, self.starts)
@@ -465,13 +537,13 @@ class RecurrentPPO(PPO):
             obs, rew, term, trunc, term_obs = env.step_t(clipped)
             done = term | trunc
             timeout = (trunc & ~term).float()
-            with torch.no_grad():
-                rew = rew + cfg.gamma * self.policy.peek_value(term_obs, self.state) * timeout
-            rew = torch.nan_to_num(rew, nan=0.0, posinf=0.0, neginf=0.0)
+            raw = torch.nan_to_num(rew, nan=0.0, posinf=0.0, neginf=0.0)
             if cfg.reward_clip > 0:
-                rew = rew.clamp(-cfg.reward_clip, cfg.reward_clip)
-            rb["rew"][t].copy_(rew); rb["done"][t].copy_(done)
-            self._ep_ret += rew
+                raw = raw.clamp(-cfg.reward_clip, cfg.reward_clip)
+            with torch.no_grad():
+                rew = self._learner_reward(raw, done, cfg.gamma * self.policy.peek_value(term_obs, self.state) * timeout)
+            rb["rew"][t].copy_(rew); rb["done"][t].copy_(done); rb["raw_sum"] += raw.sum()
+            self._ep_ret += raw
             self._ep_len += 1
             d = done.to(torch.float64)
             ep += torch.stack([(self._ep_ret.double() * d).sum(), (self._ep_len.double() * d).sum(),
@@ -485,7 +557,7 @@ class RecurrentPPO(PPO):
             _, last_value, _ = self.policy.step(self.obs, self.state, self.starts)
         adv, ret = compute_gae(rb["rew"], rb["val"], rb["done"], last_value, cfg.gamma, cfg.gae_lambda)
         rb["adv"].copy_(adv); rb["ret"].copy_(ret)
-        rb["mean_reward"].copy_(rb["rew"].mean())
+        rb["mean_reward"].copy_(rb["raw_sum"] / float(T * env.num_envs))
 
     def collect(self):
         """Rollout buffers keep their [T, envs] shape (the update replays env sequences)."""

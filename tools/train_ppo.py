@@ -60,10 +60,19 @@ def main():
 
     stats = ppo.learn(args.total_steps, log=log)
     batch.check()
+    ar = ppo.allreduce_seconds_per_step()
     if rank == 0:
         wall = time.perf_counter() - t0
         sim = sum(h["rollout_seconds"] for h in stats.history)
+        upd = sum(h["update_seconds"] for h in stats.history)
+        n_params = sum(p.numel() for p in ppo.policy.parameters())
+        steps_per_update = ppo._upd_calls / max(1, len(stats.history))
         print(json.dumps({"summary": True, "envs": args.envs, "gpus": world, "env_steps": stats.env_steps,
+                          "update_seconds_total": upd, "rollout_seconds_total": sim,
+                          "policy_parameters": n_params, "optimiser_steps_per_update": steps_per_update,
+                          "allreduce_seconds_per_optimiser_step": ar,
+                          "allreduce_share_of_update": (ar * ppo._upd_calls / upd) if upd > 0 else 0.0,
+                          "update_cuda_graph": bool(ppo.graph_update),
                           "wall_seconds": wall, "env_steps_per_sec_incl_learner": stats.env_steps / wall,
                           "env_steps_per_sec_rollout_only": stats.env_steps / sim,
                           "final_success_rate": stats.success_rate,
