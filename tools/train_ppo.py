@@ -77,6 +77,9 @@ def main():
                           "env_steps_per_sec_rollout_only": stats.env_steps / sim,
                           "final_success_rate": stats.success_rate,
                           "final_mean_episode_return": stats.mean_episode_return}), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
