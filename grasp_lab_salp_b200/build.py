@@ -24,6 +24,7 @@ UNITS = {
     "salp_kernels.cu": [],
     "salp_step_f64.cu": ["-fmad=false"],   # reference mode: no FMA contraction
     "salp_capi.cu": [],
+    "salp_policy.cu": [],
 }
 
 

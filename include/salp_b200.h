@@ -297,6 +297,18 @@ int64_t salp_sizeof_step_io(void);
  * FP32 SIMT figure). */
 int salp_probe_fp32_peak(int device, int millis, double* tflops_out);
 
+/* ---- rollout-side policy forward (no reference counterpart in src/: the reference's policies live in
+ * stable-baselines3; this is SB3's `MlpPolicy` forward as one kernel in front of salp_step) ----------
+ * weights_dev: one packed float array -- actor W1[64,D] b1[64] W2[64,64] b2[64] W3[3,64] b3[3], critic
+ * W1[64,D] b1[64] W2[64,64] b2[64] W3[1,64] b3[1], log_std[3] (row-major like torch's nn.Linear.weight);
+ * salp_mlp_packed_size(D) floats.  noise_dev: standard-normal [N,3].  Outputs: action [N,3] = mean +
+ * noise * exp(log_std), clipped [N,3] = action clipped to [low, high] (what the env gets), logp [N], value [N].
+ * action_low / action_high: host float[3]. */
+int64_t salp_mlp_packed_size(int32_t obs_dim);
+int salp_mlp_act(const float* weights_dev, int32_t obs_dim, const float* obs_dev, const float* noise_dev, int64_t n,
+                 const float* action_low, const float* action_high, float* action_dev, float* clipped_dev,
+                 float* logp_dev, float* value_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

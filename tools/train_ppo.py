@@ -78,8 +78,12 @@ def main():
                           "final_success_rate": stats.success_rate,
                           "final_mean_episode_return": stats.mean_episode_return}), flush=True)
     if world > 1:
-        import torch.distributed as dist
-        dist.destroy_process_group()
+        # (no destroy_process_group(): with NCCL collectives captured in CUDA graphs it blocked at exit on
+        #  8 GPUs; leave at once instead)
+        sys.stdout.flush()
+        if out:
+            out.close()
+        os._exit(0)
 
 
 if __name__ == "__main__":
