@@ -26,16 +26,22 @@
 struct MlpOffsets {
   int aW1, ab1, aW2, ab2, aW3, ab3, cW1, cb1, cW2, cb2, cW3, cb3, log_std, total;
 };
-static __host__ __device__ MlpOffsets mlp_offsets(int D) {
+// PAD = 1: the packed global layout; PAD = 4: the shared-memory copy, every segment starting on a
+// 16-byte boundary (the 64 x 64 layers are read with 128-bit loads)
+static __host__ __device__ MlpOffsets mlp_offsets(int D, int PAD = 1) {
   MlpOffsets o;
   int p = 0;
-  o.aW1 = p; p += MLP_H * D; o.ab1 = p; p += MLP_H; o.aW2 = p; p += MLP_H * MLP_H; o.ab2 = p; p += MLP_H;
-  o.aW3 = p; p += MLP_A * MLP_H; o.ab3 = p; p += MLP_A;
-  o.cW1 = p; p += MLP_H * D; o.cb1 = p; p += MLP_H; o.cW2 = p; p += MLP_H * MLP_H; o.cb2 = p; p += MLP_H;
-  o.cW3 = p; p += MLP_H; o.cb3 = p; p += 1;
-  o.log_std = p; p += MLP_A;
+  auto seg = [&](int& field, int count) { field = p; p += (count + PAD - 1) / PAD * PAD; };
+  seg(o.aW1, MLP_H * D); seg(o.ab1, MLP_H); seg(o.aW2, MLP_H * MLP_H); seg(o.ab2, MLP_H);
+  seg(o.aW3, MLP_A * MLP_H); seg(o.ab3, MLP_A);
+  seg(o.cW1, MLP_H * D); seg(o.cb1, MLP_H); seg(o.cW2, MLP_H * MLP_H); seg(o.cb2, MLP_H);
+  seg(o.cW3, MLP_H); seg(o.cb3, 1);
+  seg(o.log_std, MLP_A);
   o.total = p;
   return o;
+}
+__device__ __forceinline__ void stage_segment(float* sw, const float* __restrict__ w, int dst, int src, int count) {
+  for (int k = threadIdx.x; k < count; k += blockDim.x) sw[dst + k] = w[src + k];
 }
 
 // y = tanh(W2 tanh(W1 x + b1) + b2) for one thread's x; weights broadcast from shared memory
@@ -70,8 +76,14 @@ salp_mlp_act_kernel(const float* __restrict__ weights, const float* __restrict__
                     float* __restrict__ action, float* __restrict__ clipped, float* __restrict__ logp,
                     float* __restrict__ value) {
   extern __shared__ __align__(16) float sw[];
-  const MlpOffsets o = mlp_offsets(D);
-  for (int k = threadIdx.x; k < o.total; k += blockDim.x) sw[k] = weights[k];
+  const MlpOffsets g = mlp_offsets(D, 1), o = mlp_offsets(D, 4);
+  stage_segment(sw, weights, o.aW1, g.aW1, MLP_H * D); stage_segment(sw, weights, o.ab1, g.ab1, MLP_H);
+  stage_segment(sw, weights, o.aW2, g.aW2, MLP_H * MLP_H); stage_segment(sw, weights, o.ab2, g.ab2, MLP_H);
+  stage_segment(sw, weights, o.aW3, g.aW3, MLP_A * MLP_H); stage_segment(sw, weights, o.ab3, g.ab3, MLP_A);
+  stage_segment(sw, weights, o.cW1, g.cW1, MLP_H * D); stage_segment(sw, weights, o.cb1, g.cb1, MLP_H);
+  stage_segment(sw, weights, o.cW2, g.cW2, MLP_H * MLP_H); stage_segment(sw, weights, o.cb2, g.cb2, MLP_H);
+  stage_segment(sw, weights, o.cW3, g.cW3, MLP_H); stage_segment(sw, weights, o.cb3, g.cb3, 1);
+  stage_segment(sw, weights, o.log_std, g.log_std, MLP_A);
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -115,7 +127,7 @@ int salp_mlp_act(const float* weights_dev, int32_t obs_dim, const float* obs_dev
       !action_low || !action_high)
     return SALP_ERR_INVALID;
   if (obs_dim < 1 || obs_dim > SALP_OBS_BASE + 2 * SALP_MAX_OBSTACLES) return SALP_ERR_INVALID;
-  const MlpOffsets o = mlp_offsets(obs_dim);
+  const MlpOffsets o = mlp_offsets(obs_dim, 4);
   const size_t smem = sizeof(float) * (size_t)o.total;
   const unsigned grid = (unsigned)((n + 127) / 128);
   cudaStream_t s = (cudaStream_t)stream;

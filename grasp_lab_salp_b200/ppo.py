@@ -112,6 +112,14 @@ class MlpPolicy(nn.Module):
         logp = (-0.5 * noise.pow(2) - self.log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
         return a, logp, self.value(obs)
 
+    def packed(self):
+        """All rollout-side parameters as ONE float array in the layout salp_mlp_act expects
+        (include/salp_b200.h): actor W1 b1 W2 b2 W3 b3, critic W1 b1 W2 b2 W3 b3, log_std."""
+        a, c = self.actor, self.critic
+        return torch.cat([t.detach().reshape(-1) for t in (
+            a[0].weight, a[0].bias, a[2].weight, a[2].bias, a[4].weight, a[4].bias,
+            c[0].weight, c[0].bias, c[2].weight, c[2].bias, c[4].weight, c[4].bias, self.log_std)])
+
     def evaluate(self, obs, actions):
         """log-prob, entropy, value -- written out (no torch.distributions: its argument validation
         synchronises the stream, which also forbids CUDA-graph capture)."""
@@ -149,6 +157,8 @@ class PPOConfig:
                                       # the actor's clipped gradient falls below Adam's eps -- the LSTM actor then does
                                       # not move for the first ~15 M env-steps (profiles/README.md, round 1 curve).
                                       # Episode statistics are always reported on the RAW env reward.
+    fused_policy: bool = True         # MLP policy on CUDA: the rollout-side forward (both networks, sampling, log-prob,
+                                      # clip) is ONE hand-written kernel, salp_mlp_act (csrc/salp_policy.cu)
     cuda_graphs: bool = False         # MLP PPO on CUDA: replay the whole rollout and each minibatch step as CUDA graphs
     seed: int = 0
     hidden: tuple = (64, 64)
@@ -207,6 +217,17 @@ class PPO:
         self.gen.manual_seed(self._gen_seed)
         self.low = torch.tensor(self.cfg.action_low, device=self.device)
         self.high = torch.tensor(self.cfg.action_high, device=self.device)
+        self._fused = None
+        if (self.cfg.fused_policy and self.device.type == "cuda" and isinstance(self.policy, MlpPolicy)
+                and tuple(self.cfg.hidden) == (64, 64)):
+            import ctypes as C
+            from . import _lib
+            lib = _lib.load()
+            n = env.num_envs
+            assert lib.salp_mlp_packed_size(env.obs_dim) == self.policy.packed().numel()
+            self._fused = dict(lib=lib, lo=(C.c_float * 3)(*self.cfg.action_low), hi=(C.c_float * 3)(*self.cfg.action_high),
+                               a=torch.empty((n, 3), device=self.device), clipped=torch.empty((n, 3), device=self.device),
+                               logp=torch.empty(n, device=self.device), v=torch.empty(n, device=self.device), C=C)
         self.obs = env.reset_t()
         n = env.num_envs
         self._ep_ret = torch.zeros(n, device=self.device)
@@ -276,10 +297,26 @@ class PPO:
         ep = rb["ep"]            # [sum return, sum length, successes, episodes] of the episodes that ended
         ep.zero_()
         rb["raw_sum"].zero_()
+        fz = self._fused
+        if fz is not None:
+            packed = self.policy.packed()             # the weights do not change during a rollout
         for t in range(T):
-            a, logp, v = self.policy.act(self.obs, self.gen)
+            if fz is not None:
+                # ONE kernel instead of ~20 launches: both networks, sampling, log-prob, Box clip
+                noise = torch.randn((env.num_envs, 3), device=self.device, generator=self.gen)
+                C = fz["C"]
+                rc = fz["lib"].salp_mlp_act(C.c_void_p(packed.data_ptr()), env.obs_dim, C.c_void_p(self.obs.data_ptr()),
+                                            C.c_void_p(noise.data_ptr()), env.num_envs, fz["lo"], fz["hi"],
+                                            C.c_void_p(fz["a"].data_ptr()), C.c_void_p(fz["clipped"].data_ptr()),
+                                            C.c_void_p(fz["logp"].data_ptr()), C.c_void_p(fz["v"].data_ptr()),
+                                            C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+                if rc != 0:
+                    raise RuntimeError(f"salp_mlp_act failed ({rc})")
+                a, logp, v, clipped = fz["a"], fz["logp"], fz["v"], fz["clipped"]
+            else:
+                a, logp, v = self.policy.act(self.obs, self.gen)
+                clipped = torch.minimum(torch.maximum(a, self.low), self.high).float().contiguous()
             rb["obs"][t].copy_(self.obs); rb["act"][t].copy_(a); rb["logp"][t].copy_(logp); rb["val"][t].copy_(v)
-            clipped = torch.minimum(torch.maximum(a, self.low), self.high).float().contiguous()
             obs, rew, term, trunc, term_obs = env.step_t(clipped)
             done = term | trunc
             timeout = (trunc & ~term).float()

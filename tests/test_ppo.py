@@ -138,3 +138,65 @@ def test_recurrent_ppo_improves_on_gpu():
     assert last["success_rate"] > 0.45 and last["mean_episode_return"] > first["mean_episode_return"] + 100
     assert max(r["approx_kl"] for r in rows[:5]) > 1e-3       # the actor moves from the first update on
     torch.cuda.synchronize()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("obs_dim", [10, 16])
+def test_fused_mlp_forward_matches_torch(obs_dim):
+    """salp_mlp_act (csrc/salp_policy.cu: both 64-64 tanh networks, sampling, log-prob and Box clip in
+    ONE kernel) against the plain fp32 torch forward of the same MlpPolicy: 1e-5 absolute."""
+    import ctypes as C
+    import math
+    import torch
+    from grasp_lab_salp_b200 import _lib
+    from grasp_lab_salp_b200.ppo import MlpPolicy
+    lib = _lib.load()
+    torch.manual_seed(3)
+    n = 5000                                  # not a multiple of the block size
+    pol = MlpPolicy(obs_dim, 3).cuda()
+    with torch.no_grad():                     # non-trivial heads and log_std
+        pol.actor[4].weight.mul_(30.0)
+        pol.log_std.copy_(torch.tensor([-0.3, 0.1, 0.4]))
+    obs = torch.randn(n, obs_dim, device="cuda") * 2
+    noise = torch.randn(n, 3, device="cuda")
+    packed = pol.packed()
+    assert lib.salp_mlp_packed_size(obs_dim) == packed.numel()
+    a, clipped = torch.empty(n, 3, device="cuda"), torch.empty(n, 3, device="cuda")
+    logp, v = torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
+    lo, hi = (C.c_float * 3)(0.0, 0.0, -1.0), (C.c_float * 3)(1.0, 1.0, 1.0)
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    rc = lib.salp_mlp_act(p(packed), obs_dim, p(obs), p(noise), n, lo, hi, p(a), p(clipped), p(logp), p(v),
+                          C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        mean = pol.actor(obs)
+        ref_a = mean + noise * pol.log_std.exp()
+        ref_logp = (-0.5 * noise.pow(2) - pol.log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
+        ref_v = pol.value(obs)
+        ref_c = torch.minimum(torch.maximum(ref_a, torch.tensor([0.0, 0.0, -1.0], device="cuda")),
+                              torch.tensor([1.0, 1.0, 1.0], device="cuda"))
+    assert (a - ref_a).abs().max().item() < 1e-5
+    assert (clipped - ref_c).abs().max().item() < 1e-5
+    assert (logp - ref_logp).abs().max().item() < 1e-5
+    assert (v - ref_v).abs().max().item() < 1e-5
+
+
+@pytest.mark.gpu
+def test_fused_policy_rollout_equals_torch_rollout():
+    """PPO rollouts with the fused forward kernel and with the torch forward: same noise stream, same
+    simulator -> same rollout buffers up to the forward's fp32 rounding."""
+    import torch
+    from grasp_lab_salp_b200 import SalpBatch, default_params
+    from grasp_lab_salp_b200.ppo import PPO, DeviceEnv, PPOConfig
+    outs = []
+    for fused in (True, False):
+        batch = SalpBatch(2048, default_params(), seed=4)
+        algo = PPO(DeviceEnv(batch), PPOConfig(n_steps=4, batch_size=2048, seed=2, fused_policy=fused))
+        assert (algo._fused is not None) == fused
+        roll = algo.collect()
+        torch.cuda.synchronize()
+        outs.append({k: roll[k].clone() for k in ("obs", "act", "logp", "val")})
+        batch.check()
+    for k in outs[0]:
+        assert (outs[0][k] - outs[1][k]).abs().max().item() < 2e-4, k
