@@ -297,6 +297,16 @@ SALP_DEV int phase_at(const CyclePlan& c, double t) {
 SALP_DEV int plan_substeps(const CyclePlan& c, const double* time_table) {
   if (!(c.total64 == c.total64)) return 0;               // NaN total: `t < nan` is False, the loop never runs
   if (cycle_running(c, time_table[SALP_MAX_SUBSTEPS])) return -1;
+  // `running(t_k)` is monotone in k (the table increases, also after rounding to float32), and
+  // total / dt is within a couple of entries of the answer: walk from that guess (2-3 table reads
+  // instead of the 13 dependent reads of a bisection -- a microsecond of the fixed per-step cost)
+  const double g = c.total64 * 100.0;                    // 1 / dt = 100 for the reference's dt; any guess is correct, only slower
+  int k = g < 0.0 ? 0 : (g > (double)SALP_MAX_SUBSTEPS ? SALP_MAX_SUBSTEPS : (int)g);
+  if (k > 8 && k < SALP_MAX_SUBSTEPS - 8 && cycle_running(c, time_table[k - 8]) && !cycle_running(c, time_table[k + 8])) {
+    k -= 8;                                              // running(t_k) holds here
+    while (cycle_running(c, time_table[k + 1])) k++;     // last running entry
+    return k + 1;
+  }
   int lo = 0, hi = SALP_MAX_SUBSTEPS;                     // running(t_k) for k < lo; !running(t_hi)
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
