@@ -253,9 +253,26 @@ struct StepCtx {
   RandCtx rc;                 // only meaningful when SalpParams.randomization != 0
 };
 
+// The epilogue (env_step_end) reads the tail of the env's record -- episode accumulators, target,
+// obstacles -- which the prologue does not touch: after a long substep loop (or a flushed L2) those
+// lines come from DRAM on the critical path.  Ask for them now.
+SALP_HD void prefetch_record_tail(const SalpView& v, int64_t i) {
+#if defined(__CUDA_ARCH__) && SALP_STATE_AOS
+  const char* f64 = reinterpret_cast<const char*>(v.f64 + i * SALP_NUM_F64_FIELDS);
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(f64 + 8 * SALP_F_PREV_DIST));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(f64 + 8 * SALP_F_EP_SUM_TERM3));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(f64 + 8 * (SALP_NUM_F64_FIELDS - 1)));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(v.f32 + i * SALP_NUM_F32));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(v.f32 + i * SALP_NUM_F32 + SALP_NUM_F32 - 1));
+#else
+  (void)v; (void)i;
+#endif
+}
+
 SALP_HD void env_step_begin(const SalpParams& p, const SalpView& v, const SalpStepIO& io, int64_t i, StepCtx& cx,
                             Body64& b) {
   Cols c{v, i};
+  prefetch_record_tail(v, i);
   cx.a0 = io.actions[3 * i];
   cx.a1 = io.actions[3 * i + 1];
   cx.a2 = io.actions[3 * i + 2];
