@@ -239,10 +239,14 @@ class PPO:
         self.env_steps = 0
         self.iteration = 0
         self.dist_world = 1
-        try:
+        self.global_envs = n        # envs over all ranks: the loop in learn() counts with it so that ranks
+        try:                        # holding shards of different sizes still run the same number of iterations
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized():
                 self.dist_world = dist.get_world_size()
+                g = torch.tensor([n], device=self.device, dtype=torch.int64)
+                dist.all_reduce(g)
+                self.global_envs = int(g.item())
                 for p in self.policy.parameters():          # identical initial weights on every rank
                     dist.broadcast(p.data, src=0)
                 self.gen.manual_seed(self._gen_seed + 7919 * dist.get_rank())
@@ -466,10 +470,15 @@ class PPO:
             total, count = float(t[0]), float(t[1])
         return total / count if count else float("nan"), int(count)
 
+    @property
+    def env_steps_global(self) -> int:
+        """Env-steps collected over all ranks. Every rank collects the same number of rollouts, so this
+        is the same number everywhere even when the shards differ in size."""
+        return self.env_steps // self.env.num_envs * self.global_envs
+
     def learn(self, total_env_steps: int, log=None) -> PPOStats:
         stats = PPOStats()
-        per_iter = self.cfg.n_steps * self.env.num_envs * self.dist_world
-        while self.env_steps * self.dist_world < total_env_steps:
+        while self.env_steps_global < total_env_steps:
             t0 = time.perf_counter()
             roll = self.collect()
             if self.device.type == "cuda":
@@ -486,7 +495,7 @@ class PPO:
             mean_len, _ = self._reduce_stat(ep[1], ne)
             succ, _ = self._reduce_stat(ep[2], ne)
             mean_rew, _ = self._reduce_stat(float(roll["mean_reward"]), 1)
-            row = dict(iteration=self.iteration, env_steps=self.iteration * per_iter, mean_step_reward=mean_rew,
+            row = dict(iteration=self.iteration, env_steps=self.env_steps_global, mean_step_reward=mean_rew,
                        episodes=n_ep, mean_episode_return=mean_ret, mean_episode_length=mean_len, success_rate=succ,
                        rollout_seconds=t1 - t0, update_seconds=t2 - t1, **upd)
             stats.history.append(row)

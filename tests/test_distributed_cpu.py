@@ -79,3 +79,46 @@ def test_two_rank_shards_equal_the_single_process_run():
     for t in range(T + 1):
         got = np.concatenate([np.array(gathered[0][t], np.float32), np.array(gathered[1][t], np.float32)])
         np.testing.assert_array_equal(got, ref[t].astype(np.float32))
+
+
+def _ppo_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch
+    from emu_backend import emu_cdll
+    from grasp_lab_salp_b200.distributed import make_shard
+    from grasp_lab_salp_b200.ppo import PPO, HostEnv, PPOConfig
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shard = make_shard(13, seed=2, device=0, _cdll=emu_cdll())            # 7 + 6 envs: uneven shards
+    algo = PPO(HostEnv(shard), PPOConfig(n_steps=4, batch_size=8, n_epochs=2, seed=3))
+    noise = torch.randn(3, generator=algo.gen)                             # per-rank exploration noise
+    stats = algo.learn(2 * 4 * 13)
+    w = torch.cat([p.detach().reshape(-1) for p in algo.policy.parameters()])
+    gathered = [None] * world
+    dist.gather_object((w.tolist(), noise.tolist(), algo._upd_calls, stats.env_steps), gathered if rank == 0 else None, dst=0)
+    if rank == 0:
+        out.put(gathered)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_ppo_with_uneven_shards_keeps_ranks_in_step():
+    """PPO over gloo, 13 envs on 2 ranks (7 + 6): every rank issues the same number of gradient
+    all-reduces (minibatch count from the smallest shard -- an uneven count would deadlock), the
+    weights stay identical across ranks, the exploration noise differs per rank."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29900 + os.getpid() % 90
+    procs = [ctx.Process(target=_ppo_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    gathered = out.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (w0, z0, calls0, steps0), (w1, z1, calls1, steps1) = gathered
+    np.testing.assert_allclose(w0, w1, rtol=0, atol=1e-7)
+    assert calls0 == calls1 and calls0 > 0
+    assert z0 != z1
