@@ -127,13 +127,17 @@ int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& i
     order = scratch.order;
   }
   const int block = block_for(v.n);
-  // Small batches (at most one 32-env block per SM): the warp-specialised pipeline kernel
-  // (salp_pipe4_kernel.cuh), natural or K-sorted order, unless SALP_STEP_FUSED asks for the one-warp
-  // kernel.  (Two co-resident blocks share the sub-partitions and were measured slower than the
-  // fused kernel: 222 vs 192 us at 9472 envs.)
+  // Small batches: the warp-specialised pipeline kernel (salp_pipe4_kernel.cuh), natural or K-sorted
+  // order, unless SALP_STEP_FUSED asks for the one-warp kernel.  Up to one 32-env block per SM (4736
+  // envs) it is 1.27x faster than the fused kernel; with two co-resident blocks per SM, the second one
+  // with rotated warp roles, still 1.14x at 5120 and 1.07x at 8192 envs, and level at ~9150 (the
+  // producers of the two blocks share sub-partitions while the shape moves): used up to 56 envs per
+  // SM.  SALP_PIPE_BLOCKS_PER_SM=1 restores the one-block limit (experiment switch).
   const int sms = v.sm_count > 0 ? v.sm_count : 148;
   const bool pipe_ok = p.precision == SALP_PRECISION_MIXED && p.randomization == 0 && !(flags & SALP_STEP_FUSED);
-  if (pipe_ok && v.n <= (int64_t)32 * sms) {
+  static const int pipe_blocks_per_sm = [] { const char* e = getenv("SALP_PIPE_BLOCKS_PER_SM"); return e ? atoi(e) : 2; }();
+  const int64_t pipe_max_envs = (int64_t)sms * (pipe_blocks_per_sm >= 2 ? 56 : 32);
+  if (pipe_ok && v.n <= pipe_max_envs) {
     static bool configured4[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -146,12 +150,13 @@ int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& i
         return SALP_ERR_CUDA;
       if (dev >= 0 && dev < 64) configured4[dev] = true;
     }
+    const uint32_t pflags = (flags & 0x3fffffffu) | (grid_for(v.n, 32) > sms ? SALP_P4_FLAG_SHARED_SM : 0u);
     if (flags & SALP_STEP_CHECK_HANDOFF)      // (a separate kernel: the production one keeps its register allocation)
       salp_step_kernel_pipe4<true><<<grid_for(v.n, 32), SALP_P4_THREADS, pipe4_smem_bytes(p, dv.axisym != 0), stream>>>(
-          p, dv, v, io, flags, order);
+          p, dv, v, io, pflags, order);
     else
       salp_step_kernel_pipe4<false><<<grid_for(v.n, 32), SALP_P4_THREADS, pipe4_smem_bytes(p, dv.axisym != 0), stream>>>(
-          p, dv, v, io, flags, order);
+          p, dv, v, io, pflags, order);
     name = "salp_step_kernel_pipe4";
     SALP_LAUNCH_CHECK();
     return launches + 1;

@@ -26,6 +26,9 @@
 // with the same fixed 32-substep grouping of the fp32 chunk sums, and every operation is explicitly
 // rounded: bit-identical with the fused kernel (tests/test_gpu_parity.py).
 //
+// "warp r" above is a ROLE; which hardware warp takes it is decided at the top of the body (two
+// co-resident blocks per SM interleave their roles over the sub-partitions).
+//
 // Envs may be visited through a permutation (`order`, the K-sort).
 #pragma once
 #include "salp_pipe_kernel.cuh"
@@ -104,6 +107,10 @@ __device__ __forceinline__ void p4_run_chunk(int j0, int je, int K, int& dn, Ite
 // SALP_ERR_HANDOFF otherwise.  A row read before its producer wrote it, or overwritten before its
 // consumer read it, shows up as a wrong tag.  (compute-sanitizer is closed on the measurement pool;
 // this is the repo's own race evidence, tests/test_gpu_parity.py.)
+#define SALP_P4_FLAG_SHARED_SM 0x40000000u     // launcher-internal: more blocks than SMs, see the role assignment
+#define SALP_P4_MAX_SMS 256
+__device__ unsigned int salp_p4_sm_ticket[SALP_P4_MAX_SMS];
+
 template <bool AXI, bool CHECK>
 __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpDerived& dv, const SalpView& v,
                                                 const SalpStepIO& io, uint32_t flags, const int32_t* __restrict__ order,
@@ -120,7 +127,30 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
   int* tags2 = tags1 + SALP_P4_SLOTS1 * 32;
   int* tags3 = tags2 + SALP_P4_SLOTS2 * 32;
   float* tile = reinterpret_cast<float*>(smem + L::tile);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31;
+  // Role of this warp: 0 dyn, 1 kin, 2 coefs R, 3 front, one per SM sub-partition.  With two blocks
+  // per SM (4737-8288 envs; flags bit 30, set by the launcher) the block that arrives second on its SM
+  // rotates its roles by two, so that during the coast -- when only dyn and kin are busy -- the four
+  // busy warps of the two co-resident blocks sit on four different sub-partitions: 110 instead of 185
+  // cycles per coast substep.  Two things had to be measured to get there: the sub-partition of a warp
+  // is its hardware slot (%warpid & 3), which for the second block on an SM is NOT threadIdx.x / 32 & 3;
+  // and "second on its SM" is not blockIdx.x / #SMs & 1 once every SM holds two blocks, so the blocks
+  // draw a ticket from a per-SM counter (never reset: co-resident blocks draw consecutive tickets).
+  const int widx = threadIdx.x >> 5;
+  int warp = widx;
+  if (flags & SALP_P4_FLAG_SHARED_SM) {
+    __shared__ int slot_of_warp[4];
+    __shared__ unsigned ticket;
+    unsigned hw, sm;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    if (lane == 0) slot_of_warp[widx] = (int)(hw & 3u);
+    if (threadIdx.x == 0) ticket = atomicAdd(&salp_p4_sm_ticket[sm & (SALP_P4_MAX_SMS - 1)], 1u);
+    __syncthreads();
+    const int seen = (1 << slot_of_warp[0]) | (1 << slot_of_warp[1]) | (1 << slot_of_warp[2]) | (1 << slot_of_warp[3]);
+    const int base = seen == 15 ? slot_of_warp[widx] : widx;
+    warp = (base + 2 * (int)(ticket & 1u)) & 3;
+  }
   const int64_t tid = (int64_t)blockIdx.x * 32 + lane;
   const bool live = tid < v.n;
   const int64_t i = live ? (order ? (int64_t)order[tid] : tid) : 0;
@@ -403,7 +433,7 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
 }
 
 template <bool CHECK>
-__global__ void __launch_bounds__(SALP_P4_THREADS, 1)
+__global__ void __launch_bounds__(SALP_P4_THREADS, 2)
 salp_step_kernel_pipe4(const __grid_constant__ SalpParams p, const __grid_constant__ SalpDerived dv,
                        const __grid_constant__ SalpView v, const __grid_constant__ SalpStepIO io, uint32_t flags,
                        const int32_t* __restrict__ order) {

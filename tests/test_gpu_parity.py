@@ -304,6 +304,31 @@ def test_axisymmetric_form_equals_general_form(n, pipeline):
     b.check()
 
 
+@pytest.mark.parametrize("n", [6001, 8288])
+def test_pipeline_kernel_two_blocks_per_sm_matches_fused_kernel(n):
+    """4737-8288 envs: two pipeline blocks share an SM and the second one rotates its warp roles
+    (hardware warp slot + per-SM ticket, salp_pipe4_kernel.cuh).  Whatever roles the warps draw, the
+    result is the fused kernel's, bit for bit; the hand-off tags are checked on the way."""
+    from grasp_lab_salp_b200.params import FIELDS
+    T = 6
+    g = load_golden("ref_random.npz")
+    acts = uniform_actions(np.random.default_rng(21), T, n)
+    acts[2, 64:128] = 0.0
+    pipe, fused = SalpBatch(n, golden_params(g), seed=4), SalpBatch(n, golden_params(g), seed=4)
+    np.testing.assert_array_equal(pipe.reset(), fused.reset())
+    for t in range(T):
+        r1 = pipe.step(acts[t], auto_reset=True, check_handoff=(t % 2 == 0))
+        assert pipe.last_step_kernel == "salp_step_kernel_pipe4"
+        r2 = fused.step(acts[t], auto_reset=True, pipeline=False)
+        assert fused.last_step_kernel != "salp_step_kernel_pipe4"
+        for x, y in zip(r1, r2):
+            np.testing.assert_array_equal(x, y)
+        np.testing.assert_array_equal(pipe.substeps, fused.substeps)
+    pipe.check()
+    for col in FIELDS:
+        np.testing.assert_array_equal(pipe.get_state(col), fused.get_state(col), err_msg=col)
+
+
 def test_pipeline_kernel_is_deterministic_at_full_size():
     """Two handles, same seed, same actions, BASELINE's 4096 envs (every SM busy with one
     three-warp block), 40 free-running steps: bit-identical outputs and state.  A missed hand-off

@@ -21,7 +21,9 @@ a348 = z.clone(); a348[..., 0] = 1.0
 a1348 = a348.clone(); a1348[..., 1] = 1.0
 g = torch.Generator(device=dev); g.manual_seed(1234)
 u = torch.rand((16, n, 3), generator=g, device=dev); u[..., 2] = u[..., 2] * 2 - 1
+only = os.environ.get("DIAG_ONLY")
 for label, kw in (("default", {}), ("fused", dict(pipeline=False))):
+    if only and label != only: continue
     t0, k = run(z, **kw); tA, _ = run(a348, **kw); tB, _ = run(a1348, **kw); tu, _ = run(u, **kw)
     print(f"{label:8s} [{k}] n={n}: K=0 {t0:6.1f} us | moving {1965*(tA-t0)/348:6.1f} cyc/substep | coast {1965*(tB-tA)/1000:6.1f} cyc/substep | "
           f"K=1348 {tB:6.1f} us | uniform random {tu:6.1f} us", flush=True)
