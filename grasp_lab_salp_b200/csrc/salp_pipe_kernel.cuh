@@ -19,8 +19,8 @@ __device__ __forceinline__ void pipe_bar_sync(int id, int threads = 64) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 // (no fence: a completed barrier orders the shared-memory accesses its participants made before
-//  arriving -- the producer/consumer idiom of the PTX ISA's bar.arrive / bar.sync example;
-//  compute-sanitizer racecheck summary: profiles/r02_sanitizer_racecheck.txt)
+//  arriving -- the producer/consumer idiom of the PTX ISA's bar.arrive / bar.sync example; the
+//  hand-offs are checked by the tag planes of SALP_STEP_CHECK_HANDOFF, salp_pipe4_kernel.cuh)
 __device__ __forceinline__ void pipe_bar_arrive(int id, int threads = 64) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
