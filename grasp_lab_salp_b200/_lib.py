@@ -59,6 +59,13 @@ PROTOTYPES = {
     "salp_mlp_packed_size": (C.c_int64, [C.c_int32]),
     "salp_mlp_act": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_float),
                                C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "salp_lstm_weight_bytes": (C.c_int64, []),
+    "salp_lstm_scratch_bytes": (C.c_int64, [C.c_int64]),
+    "salp_lstm_pack_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "salp_lstm_cell": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "salp_lstm_check": (C.c_int, []),
 }
 
 ABI_VERSION = 1        # SALP_ABI_VERSION of include/salp_b200.h this binding mirrors

@@ -25,6 +25,7 @@ UNITS = {
     "salp_step_f64.cu": ["-fmad=false"],   # reference mode: no FMA contraction
     "salp_capi.cu": [],
     "salp_policy.cu": [],
+    "salp_lstm.cu": [],                    # tcgen05 / TMA LSTM cell (needs the sm_100a target)
 }
 
 

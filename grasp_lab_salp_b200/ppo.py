@@ -158,7 +158,8 @@ class PPOConfig:
                                       # not move for the first ~15 M env-steps (profiles/README.md, round 1 curve).
                                       # Episode statistics are always reported on the RAW env reward.
     fused_policy: bool = True         # MLP policy on CUDA: the rollout-side forward (both networks, sampling, log-prob,
-                                      # clip) is ONE hand-written kernel, salp_mlp_act (csrc/salp_policy.cu)
+                                      # clip) is ONE hand-written kernel, salp_mlp_act (csrc/salp_policy.cu); LSTM policy
+                                      # on CUDA: both rollout-side LSTM cells run on the tensor cores (csrc/salp_lstm.cu)
     cuda_graphs: bool = False         # MLP PPO on CUDA: replay the whole rollout and each minibatch step as CUDA graphs
     seed: int = 0
     hidden: tuple = (64, 64)
@@ -549,9 +550,44 @@ class RecurrentPPO(PPO):
 
     def __init__(self, env, config: PPOConfig | None = None, policy: LstmPolicy | None = None):
         cfg = config or PPOConfig(n_steps=32, batch_size=32 * 512)
-        super().__init__(env, cfg, policy or LstmPolicy(env.obs_dim, 3, hidden=cfg.hidden))
+        if policy is None:
+            torch.manual_seed(cfg.seed)           # (the base class seeds only after its arguments are built)
+            policy = LstmPolicy(env.obs_dim, 3, hidden=cfg.hidden)
+        super().__init__(env, cfg, policy)
         self.state = self.policy.initial_state(env.num_envs, self.device)
         self.starts = torch.ones(env.num_envs, dtype=torch.bool, device=self.device)
+        # rollout-side LSTM cells on the tensor cores (csrc/salp_lstm.cu): gate GEMM in bf16 with tcgen05,
+        # cell update fused behind it; the learner keeps the fp32 torch cells (autograd)
+        self._lstm_fused = None
+        if (cfg.fused_policy and self.device.type == "cuda" and self.policy.lstm_hidden == 256
+                and env.obs_dim <= 64):
+            from .lstm import LstmCellB200
+            n = env.num_envs
+            self._lstm_fused = dict(actor=LstmCellB200(self.policy.lstm_actor, n), critic=LstmCellB200(self.policy.lstm_critic, n),
+                                    h=torch.empty((n, 256), device=self.device), c=torch.empty((n, 256), device=self.device))
+
+    def _policy_step(self, obs, starts):
+        """One rollout step of the policy on self.state (updated in place): (action mean, value)."""
+        fz = self._lstm_fused
+        if fz is None:
+            mean, v, new_state = self.policy.step(obs, self.state, starts)
+            for dst, src in zip(self.state, new_state):
+                dst.copy_(src)
+            return mean, v
+        ha, ca, hc, cc = self.state
+        fz["actor"].step(obs, starts, ha, ca)
+        fz["critic"].step(obs, starts, hc, cc)
+        return self.policy.actor(ha), self.policy.critic(hc).squeeze(-1)
+
+    def _peek_value(self, obs, starts=None):
+        """V(obs) from the critic's current state WITHOUT advancing it (bootstrap values)."""
+        fz = self._lstm_fused
+        if fz is None:
+            if starts is None:
+                return self.policy.peek_value(obs, self.state)
+            return self.policy.step(obs, self.state, starts)[1]
+        h, _ = fz["critic"].step(obs.contiguous(), starts, self.state[2], self.state[3], fz["h"], fz["c"])
+        return self.policy.critic(h).squeeze(-1)
 
     def _alloc_rollout(self):
         super()._alloc_rollout()
@@ -569,11 +605,12 @@ class RecurrentPPO(PPO):
         ep = rb["ep"]
         ep.zero_()
         rb["raw_sum"].zero_()
+        if self._lstm_fused is not None:                # the weights do not change during a rollout
+            self._lstm_fused["actor"].pack()
+            self._lstm_fused["critic"].pack()
         for t in range(T):
             with torch.no_grad():
-                mean, v, new_state = self.policy.step(self.obs, self.state, self.starts)
-                for dst, src in zip(self.state, new_state):
-                    dst.copy_(src)
+                mean, v = self._policy_step(self.obs, self.starts)
                 noise = torch.randn(mean.shape, device=self.device, generator=self.gen)
                 a = mean + noise * self.policy.log_std.exp()
                 logp = (-0.5 * noise.pow(2) - self.policy.log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
@@ -587,7 +624,7 @@ class RecurrentPPO(PPO):
             if cfg.reward_clip > 0:
                 raw = raw.clamp(-cfg.reward_clip, cfg.reward_clip)
             with torch.no_grad():
-                rew = self._learner_reward(raw, done, cfg.gamma * self.policy.peek_value(term_obs, self.state) * timeout)
+                rew = self._learner_reward(raw, done, cfg.gamma * self._peek_value(term_obs) * timeout)
             rb["rew"][t].copy_(rew); rb["done"][t].copy_(done); rb["raw_sum"] += raw.sum()
             self._ep_ret += raw
             self._ep_len += 1
@@ -600,7 +637,7 @@ class RecurrentPPO(PPO):
             self.obs.copy_(obs)
             self.starts.copy_(done)
         with torch.no_grad():
-            _, last_value, _ = self.policy.step(self.obs, self.state, self.starts)
+            last_value = self._peek_value(self.obs, self.starts)
         adv, ret = compute_gae(rb["rew"], rb["val"], rb["done"], last_value, cfg.gamma, cfg.gae_lambda)
         rb["adv"].copy_(adv); rb["ret"].copy_(ret)
         rb["mean_reward"].copy_(rb["raw_sum"] / float(T * env.num_envs))

@@ -309,6 +309,28 @@ int salp_mlp_act(const float* weights_dev, int32_t obs_dim, const float* obs_dev
                  const float* action_low, const float* action_high, float* action_dev, float* clipped_dev,
                  float* logp_dev, float* value_dev, void* stream);
 
+/* ---- rollout-side LSTM cell on the tensor cores (sb3_contrib RecurrentPPO's MlpLstmPolicy as the
+ * reference configures it, src/train_robot_recurrent_ppo.py:100-105: lstm_hidden_size = 256, separate
+ * actor / critic LSTMs on the flattened observation; the episode-start state reset is sb3_contrib's
+ * _process_sequence).  One step of torch.nn.LSTMCell(obs_dim, 256) for N envs:
+ *     gates = obs W_ih^T + (h keep) W_hh^T + b_ih + b_hh      keep[e] = starts[e] ? 0 : 1
+ *     i, f, o = sigmoid; g = tanh; c' = f (c keep) + i g; h' = o tanh(c')        (gate order i, f, g, o)
+ * as a bf16 x bf16 -> fp32 tcgen05 GEMM (TMA operands, TMEM accumulator) with the cell update fused
+ * behind it (csrc/salp_lstm.cu).  hidden must be 256, obs_dim <= 64.
+ * salp_lstm_pack_weights: once per set of weights -- permutes / rounds [W_hh | W_ih] into
+ *   packed_dev (salp_lstm_weight_bytes() bytes) and b_ih + b_hh into bias_dev (float[1024]).
+ * salp_lstm_cell: h / c [N, 256] fp32, in place allowed (h_out == h_in, c_out == c_in); starts_dev: N
+ *   bytes (torch.bool) or NULL; scratch_dev: salp_lstm_scratch_bytes(N) bytes, 16-byte aligned.
+ * salp_lstm_check: synchronises; SALP_ERR_CUDA if a kernel gave up waiting on one of its barriers. */
+int64_t salp_lstm_weight_bytes(void);
+int64_t salp_lstm_scratch_bytes(int64_t n);
+int salp_lstm_pack_weights(const float* w_ih_dev, const float* w_hh_dev, const float* b_ih_dev, const float* b_hh_dev,
+                           int32_t obs_dim, int32_t hidden, void* packed_dev, float* bias_dev, void* stream);
+int salp_lstm_cell(const void* packed_dev, const float* bias_dev, const float* obs_dev, const uint8_t* starts_dev,
+                   const float* h_in_dev, const float* c_in_dev, float* h_out_dev, float* c_out_dev, void* scratch_dev,
+                   int64_t n, int32_t obs_dim, int32_t hidden, void* stream);
+int salp_lstm_check(void);
+
 #ifdef __cplusplus
 }
 #endif

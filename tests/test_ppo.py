@@ -200,3 +200,93 @@ def test_fused_policy_rollout_equals_torch_rollout():
         batch.check()
     for k in outs[0]:
         assert (outs[0][k] - outs[1][k]).abs().max().item() < 2e-4, k
+
+
+def _lstm_cell_reference(cell, obs, starts, h, c, bf16_operands):
+    """float64 restatement of torch.nn.LSTMCell with sb3_contrib's episode-start reset; with
+    bf16_operands the GEMM operands are rounded exactly as csrc/salp_lstm.cu rounds them."""
+    keep = (~starts).double().unsqueeze(-1)
+    r = (lambda t: t.float().bfloat16().double()) if bf16_operands else (lambda t: t.double())
+    hk = (h.double() * keep).float()
+    g = r(obs) @ r(cell.weight_ih).T + r(hk) @ r(cell.weight_hh).T + (cell.bias_ih.float() + cell.bias_hh.float()).double()
+    i, f, gg, o = g.chunk(4, dim=1)
+    c2 = torch.sigmoid(f) * (c.double() * keep) + torch.sigmoid(i) * torch.tanh(gg)
+    return torch.sigmoid(o) * torch.tanh(c2), c2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,obs_dim", [(1, 10), (100, 10), (4096 + 37, 10), (640, 16), (300, 64)])
+def test_tensor_core_lstm_cell_matches_torch(n, obs_dim):
+    """salp_lstm_cell (csrc/salp_lstm.cu: bf16 tcgen05 gate GEMM + fused cell update) against
+    torch.nn.LSTMCell.  Two bars: (1) against a float64 cell fed the SAME bf16-rounded operands the
+    kernel's arithmetic is exact up to fp32 accumulation: 2e-5 absolute; (2) against the plain fp32
+    torch cell the difference is the bf16 rounding of h, obs and the weights: 2e-2 absolute on h and c
+    (measured 2-5e-3 with 1.5x-scaled default-initialised weights)."""
+    from torch import nn
+    from grasp_lab_salp_b200.lstm import LstmCellB200
+    torch.manual_seed(n + obs_dim)
+    cell = nn.LSTMCell(obs_dim, 256).cuda()
+    with torch.no_grad():
+        for p in cell.parameters():
+            p.mul_(1.5)
+    obs = torch.randn(n, obs_dim, device="cuda")
+    h = torch.tanh(torch.randn(n, 256, device="cuda"))
+    c = torch.randn(n, 256, device="cuda")
+    starts = torch.rand(n, device="cuda") < 0.2
+    fused = LstmCellB200(cell, n)
+    h1, c1 = torch.full_like(h, float("nan")), torch.full_like(c, float("nan"))
+    fused.step(obs, starts, h, c, h1, c1)
+    fused.check()
+    with torch.no_grad():
+        hb, cb = _lstm_cell_reference(cell, obs, starts, h, c, True)
+        assert (h1.double() - hb).abs().max().item() < 2e-5
+        assert (c1.double() - cb).abs().max().item() < 2e-5
+        keep = (~starts).float().unsqueeze(-1)
+        ht, ct = cell(obs, (h * keep, c * keep))
+        assert (h1 - ht).abs().max().item() < 2e-2
+        assert (c1 - ct).abs().max().item() < 2e-2
+        # in place, and without a reset mask
+        h2, c2 = h.clone(), c.clone()
+        fused.step(obs, starts, h2, c2)
+        assert torch.equal(h2, h1) and torch.equal(c2, c1)
+        fused.step(obs, None, h, c, h1, c1)
+        hn, cn = _lstm_cell_reference(cell, obs, torch.zeros_like(starts), h, c, True)
+        assert (h1.double() - hn).abs().max().item() < 2e-5 and (c1.double() - cn).abs().max().item() < 2e-5
+        # new weights are picked up by pack()
+        cell.weight_hh.mul_(0.5)
+        fused.pack()
+        fused.step(obs, starts, h, c, h1, c1)
+        hb, _ = _lstm_cell_reference(cell, obs, starts, h, c, True)
+        assert (h1.double() - hb).abs().max().item() < 2e-5
+    fused.check()
+
+
+@pytest.mark.gpu
+def test_recurrent_rollout_on_tensor_core_cells_tracks_torch_rollout():
+    """RecurrentPPO rollouts with the tcgen05 LSTM cells and with the fp32 torch cells from the same
+    seeds: the first step agrees to the bf16 tolerance of the cell (values, action means through the
+    64-64 heads), and the stored log-probs are those of the sampled actions under the rollout's own
+    policy (importance ratio of the learner's fp32 replay at epoch 0: 1 +- 5 %)."""
+    from grasp_lab_salp_b200 import SalpBatch, default_params
+    from grasp_lab_salp_b200.ppo import DeviceEnv, PPOConfig, RecurrentPPO
+    outs = []
+    for fused in (True, False):
+        batch = SalpBatch(1024, default_params(), seed=4)
+        algo = RecurrentPPO(DeviceEnv(batch), PPOConfig(n_steps=8, batch_size=8 * 1024, seed=2, fused_policy=fused))
+        assert (algo._lstm_fused is not None) == fused
+        roll = algo.collect()
+        torch.cuda.synchronize()
+        if fused:
+            algo._lstm_fused["actor"].check()
+            with torch.no_grad():                 # the learner's fp32 replay of the bf16 rollout
+                state = roll["init_state"]
+                for t in range(8):
+                    m, v, state = algo.policy.step(roll["obs"][t], state, roll["starts"][t])
+                    lp = torch.distributions.Normal(m, algo.policy.log_std.exp()).log_prob(roll["act"][t]).sum(-1)
+                    assert (lp - roll["logp"][t]).abs().max().item() < 0.05
+                    assert (v - roll["val"][t]).abs().max().item() < 0.05
+        outs.append({k: roll[k].clone() for k in ("obs", "act", "logp", "val")})
+        batch.check()
+    assert torch.equal(outs[0]["obs"][0], outs[1]["obs"][0])
+    assert (outs[0]["val"][0] - outs[1]["val"][0]).abs().max().item() < 2e-2
+    assert (outs[0]["act"][0] - outs[1]["act"][0]).abs().max().item() < 2e-2
