@@ -37,11 +37,13 @@
 #define LSTM_BN 128                      // gate columns per tile (UMMA N): 4 gates x 32 units
 #define LSTM_UNITS (LSTM_BN / 4)
 #define LSTM_BK 64                       // bf16 per 128-byte swizzle row
-#define LSTM_NKB (LSTM_KP / LSTM_BK)     // 5 K blocks, all resident: no ring reuse, every barrier fires once
+#define LSTM_NKB (LSTM_KP / LSTM_BK)     // 5 K blocks through a ring of LSTM_STAGES shared-memory stages
+#define LSTM_STAGES 2                    // 2 x 32 KB: three CTAs per SM, so one tile's epilogue overlaps the
+                                         // loads and MMAs of its neighbours (TMEM: 3 x 128 of 512 columns)
 #define LSTM_UK 16                       // K of one tcgen05.mma.kind::f16
 #define LSTM_STAGE_A (LSTM_BM * LSTM_BK * 2)
 #define LSTM_STAGE_B (LSTM_BN * LSTM_BK * 2)
-#define LSTM_SMEM (LSTM_NKB * (LSTM_STAGE_A + LSTM_STAGE_B) + 1024)
+#define LSTM_SMEM (LSTM_STAGES * (LSTM_STAGE_A + LSTM_STAGE_B) + 1024)
 #define LSTM_THREADS 192                 // warp 0 TMA, warp 1 TMEM + MMA, warps 2-5 epilogue
 #define LSTM_TMEM_COLS 128
 
@@ -168,17 +170,21 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// MUFU.EX2 + MUFU.RCP forms (absolute error ~2e-7, saturating correctly at +-inf): the libm expf / tanhf
+// paths made the epilogue ~200 instructions per hidden unit
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 
 // ------------------------------------------------------------------------------------------------
 // the cell: gates = A W^T (tcgen05), then the element-wise update from TMEM
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(LSTM_THREADS, 1)
+__global__ void __launch_bounds__(LSTM_THREADS, 3)
 salp_lstm_cell_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                       const float* __restrict__ bias_p, const uint8_t* __restrict__ starts,
-                      const float* __restrict__ c_in, float* __restrict__ h_out, float* __restrict__ c_out, int64_t n) {
+                      const float* c_in, float* h_out, float* c_out, int64_t n) {   // (c_out may alias c_in)
   extern __shared__ uint8_t lstm_smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[LSTM_NKB];
+  __shared__ __align__(8) uint64_t bar_full[LSTM_STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[LSTM_STAGES];
   __shared__ __align__(8) uint64_t bar_acc;
   __shared__ uint32_t tmem_base_slot;
   __shared__ float bias_s[LSTM_BN];
@@ -187,10 +193,13 @@ salp_lstm_cell_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   const int m0 = blockIdx.x * LSTM_BM;           // first env of the tile
   const int tile_n = blockIdx.y;                 // 32 hidden units x 4 gates
   const uint32_t smem0 = (smem_u32(lstm_smem_raw) + 1023u) & ~1023u;   // swizzle atoms want 1024-byte alignment
-  const uint32_t smem_a = smem0, smem_b = smem0 + LSTM_NKB * LSTM_STAGE_A;
+  const uint32_t smem_a = smem0, smem_b = smem0 + LSTM_STAGES * LSTM_STAGE_A;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < LSTM_NKB; s++) mbar_init(smem_u32(&bar_full[s]), 1);
+    for (int s = 0; s < LSTM_STAGES; s++) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
     mbar_init(smem_u32(&bar_acc), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -210,27 +219,36 @@ salp_lstm_cell_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
-      for (int s = 0; s < LSTM_NKB; s++) {
+      // K block kb goes to stage kb % STAGES; a stage is refilled once the MMAs that read it have
+      // completed (tcgen05.commit on bar_empty).  Phase of the n-th use of a barrier: n & 1.
+      for (int kb = 0; kb < LSTM_NKB; kb++) {
+        const int s = kb % LSTM_STAGES;
+        if (kb >= LSTM_STAGES && !mbar_wait(smem_u32(&bar_empty[s]), (uint32_t)(kb / LSTM_STAGES - 1) & 1u)) {
+          atomicExch(&salp_lstm_status_word, 3);
+          break;
+        }
         const uint32_t bar = smem_u32(&bar_full[s]);
         mbar_expect_tx(bar, LSTM_STAGE_A + LSTM_STAGE_B);
-        tma_load_2d(smem_a + s * LSTM_STAGE_A, &map_a, bar, s * LSTM_BK, m0);
-        tma_load_2d(smem_b + s * LSTM_STAGE_B, &map_w, bar, s * LSTM_BK, tile_n * LSTM_BN);
+        tma_load_2d(smem_a + s * LSTM_STAGE_A, &map_a, bar, kb * LSTM_BK, m0);
+        tma_load_2d(smem_b + s * LSTM_STAGE_B, &map_w, bar, kb * LSTM_BK, tile_n * LSTM_BN);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(LSTM_BM, LSTM_BN);
       bool ok = true;
-      for (int s = 0; s < LSTM_NKB && ok; s++) {
-        ok = mbar_wait(smem_u32(&bar_full[s]), 0);
+      for (int kb = 0; kb < LSTM_NKB; kb++) {
+        const int s = kb % LSTM_STAGES;
+        ok = mbar_wait(smem_u32(&bar_full[s]), (uint32_t)(kb / LSTM_STAGES) & 1u);
         if (!ok) break;
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < LSTM_BK / LSTM_UK; k++) {
           const uint64_t da = umma_desc_sw128(smem_a + s * LSTM_STAGE_A + k * LSTM_UK * 2);
           const uint64_t db = umma_desc_sw128(smem_b + s * LSTM_STAGE_B + k * LSTM_UK * 2);
-          umma_bf16(tmem, da, db, idesc, (s | k) != 0 ? 1u : 0u);
+          umma_bf16(tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
         }
+        if (kb + LSTM_STAGES < LSTM_NKB) umma_commit(smem_u32(&bar_empty[s]));   // stage s may be refilled
       }
       if (!ok) atomicExch(&salp_lstm_status_word, 1);
       umma_commit(smem_u32(&bar_acc));           // arrives when every MMA above has completed
@@ -242,12 +260,23 @@ salp_lstm_cell_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const int row = q * 32 + lane;
     const int64_t e = (int64_t)m0 + row;
     const bool live = e < n;
+    // the env's 32 cell states of this tile (one 128-byte line), requested BEFORE the wait for the MMAs
+    const size_t off = (size_t)(live ? e : 0) * LSTM_H + (size_t)tile_n * LSTM_UNITS;
+    float4 cprev[LSTM_UNITS / 4];
+#pragma unroll
+    for (int k = 0; k < LSTM_UNITS / 4; k++)
+      cprev[k] = live ? *(reinterpret_cast<const float4*>(c_in + off) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float keep = (live && starts && starts[e]) ? 0.f : 1.f;
     if (!mbar_wait(smem_u32(&bar_acc), 0)) atomicExch(&salp_lstm_status_word, 2);
     tc_fence_after();
-    const float keep = (live && starts && starts[e]) ? 0.f : 1.f;
-    const size_t off = (size_t)(live ? e : 0) * LSTM_H + (size_t)tile_n * LSTM_UNITS;
+    // Every MMA has completed, so the operand stages are free: each warp stages its 32 x 32 tiles of
+    // h' and c' there ([row][16-byte chunk ^ (row & 7)]: conflict-free both ways) and writes them out
+    // with consecutive lanes on consecutive 16 bytes -- four full 128-byte lines per store instruction
+    // instead of 32 scattered 16-byte pieces.
+    float4* st_h = reinterpret_cast<float4*>(lstm_smem_raw + (smem0 - smem_u32(lstm_smem_raw))) + q * 512;
+    float4* st_c = st_h + 256;
     const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
+#pragma unroll
     for (int j = 0; j < LSTM_UNITS; j += 8) {
       float gi[8], gf[8], gg[8], go[8];
       tmem_ld8(t_row + 0 * LSTM_UNITS + j, gi);
@@ -255,29 +284,33 @@ salp_lstm_cell_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       tmem_ld8(t_row + 2 * LSTM_UNITS + j, gg);
       tmem_ld8(t_row + 3 * LSTM_UNITS + j, go);
       tmem_ld_wait();
-      float cp[8], hn[8], cn[8];
-      if (live) {
-        const float4 a = *reinterpret_cast<const float4*>(c_in + off + j);
-        const float4 b = *reinterpret_cast<const float4*>(c_in + off + j + 4);
-        cp[0] = a.x; cp[1] = a.y; cp[2] = a.z; cp[3] = a.w; cp[4] = b.x; cp[5] = b.y; cp[6] = b.z; cp[7] = b.w;
-      } else {
-#pragma unroll
-        for (int u = 0; u < 8; u++) cp[u] = 0.f;
-      }
+      const float cp[8] = {cprev[j / 4].x,     cprev[j / 4].y,     cprev[j / 4].z,     cprev[j / 4].w,
+                           cprev[j / 4 + 1].x, cprev[j / 4 + 1].y, cprev[j / 4 + 1].z, cprev[j / 4 + 1].w};
+      float hn[8], cn[8];
 #pragma unroll
       for (int u = 0; u < 8; u++) {
         const float i_ = sigmoidf_(gi[u] + bias_s[0 * LSTM_UNITS + j + u]);
         const float f_ = sigmoidf_(gf[u] + bias_s[1 * LSTM_UNITS + j + u]);
-        const float g_ = tanhf(gg[u] + bias_s[2 * LSTM_UNITS + j + u]);
+        const float g_ = tanhf_(gg[u] + bias_s[2 * LSTM_UNITS + j + u]);
         const float o_ = sigmoidf_(go[u] + bias_s[3 * LSTM_UNITS + j + u]);
         cn[u] = fmaf(f_, cp[u] * keep, i_ * g_);
-        hn[u] = o_ * tanhf(cn[u]);
+        hn[u] = o_ * tanhf_(cn[u]);
       }
-      if (live) {
-        *reinterpret_cast<float4*>(c_out + off + j) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-        *reinterpret_cast<float4*>(c_out + off + j + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
-        *reinterpret_cast<float4*>(h_out + off + j) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-        *reinterpret_cast<float4*>(h_out + off + j + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+      const int ch = j / 4, sw = lane & 7;
+      st_c[lane * 8 + (ch ^ sw)] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+      st_c[lane * 8 + ((ch + 1) ^ sw)] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+      st_h[lane * 8 + (ch ^ sw)] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+      st_h[lane * 8 + ((ch + 1) ^ sw)] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+      const int r = it * 4 + (lane >> 3), ch = lane & 7;
+      const int64_t er = (int64_t)m0 + q * 32 + r;
+      if (er < n) {
+        const size_t o = (size_t)er * LSTM_H + (size_t)tile_n * LSTM_UNITS + ch * 4;
+        *reinterpret_cast<float4*>(h_out + o) = st_h[r * 8 + (ch ^ (r & 7))];
+        *reinterpret_cast<float4*>(c_out + o) = st_c[r * 8 + (ch ^ (r & 7))];
       }
     }
   }
