@@ -56,6 +56,7 @@ PROTOTYPES = {
     "salp_sizeof_params": (C.c_int64, []),
     "salp_sizeof_step_io": (C.c_int64, []),
     "salp_probe_fp32_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "salp_debug_p4_stamps": (C.c_int, [C.POINTER(C.c_longlong)]),
     "salp_mlp_packed_size": (C.c_int64, [C.c_int32]),
     "salp_mlp_act": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_float),
                                C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -232,7 +232,7 @@ class SalpBatch:
         return bufs["obs"]
 
     def step_device(self, actions, auto_reset: bool = True, sort_by_k: bool = False, extras: bool = False,
-                    pipeline=None, generic: bool = False):
+                    pipeline=None, generic: bool = False, extra_flags: int = 0):
         """actions: float32 CUDA tensor [N,3] on this batch's device.  Asynchronous on the current
         torch stream.  Returns (obs, reward, terminated, truncated) device tensors (reused every
         call); ``self.dev["terminal_obs"]`` etc. hold the rest."""
@@ -253,7 +253,7 @@ class SalpBatch:
         io.episode_metrics = bufs["metrics"].data_ptr() if extras else None
         flags = ((STEP_AUTORESET if auto_reset else 0) | (STEP_SORT_BY_K if sort_by_k else 0)
                  | (0 if pipeline is None else (STEP_PIPELINE if pipeline else STEP_FUSED))
-                 | (STEP_GENERIC if generic else 0))
+                 | (STEP_GENERIC if generic else 0) | int(extra_flags))
         self._check(self._L.salp_step(self._h, C.byref(io), flags, self._stream_ptr(self.device)))
         return bufs["obs"], bufs["reward"], bufs["terminated"], bufs["truncated"]
 

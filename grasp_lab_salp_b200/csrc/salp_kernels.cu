@@ -197,3 +197,11 @@ int salp_launch_ffma_probe(float* scratch, int blocks, int iters, cudaStream_t s
   SALP_LAUNCH_CHECK();
   return 1;
 }
+
+// Diagnostic (tools/diag_stamps.py): the clock64() stamps block 0's dyn warp took in the last pipeline
+// step launched with flag bit 29 (salp_pipe4_kernel.cuh: P4_STAMP), plus K_max and W of that block.
+extern "C" int salp_debug_p4_stamps(long long* out16) {
+  if (!out16) return SALP_ERR_INVALID;
+  if (cudaDeviceSynchronize() != cudaSuccess) return SALP_ERR_CUDA;
+  return cudaMemcpyFromSymbol(out16, salp_p4_stamps, sizeof(long long) * 16) == cudaSuccess ? SALP_OK : SALP_ERR_CUDA;
+}

@@ -110,6 +110,14 @@ __device__ __forceinline__ void p4_run_chunk(int j0, int je, int K, int& dn, Ite
 #define SALP_P4_FLAG_SHARED_SM 0x40000000u     // launcher-internal: more blocks than SMs, see the role assignment
 #define SALP_P4_MAX_SMS 256
 __device__ unsigned int salp_p4_sm_ticket[SALP_P4_MAX_SMS];
+// diagnostic (tools/diag_stamps.py): with flag bit 29 the dyn warp of block 0 records clock64() at the
+// boundaries of prologue / substep loops / epilogue; salp_debug_p4_stamps() reads them back
+#define SALP_P4_FLAG_STAMPS 0x20000000u
+__device__ long long salp_p4_stamps[16];
+#define P4_STAMP(k)                                                                          \
+  do {                                                                                       \
+    if ((flags & SALP_P4_FLAG_STAMPS) && blockIdx.x == 0 && warp == 0 && lane == 0) salp_p4_stamps[k] = clock64(); \
+  } while (0)
 
 template <bool AXI, bool CHECK>
 __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpDerived& dv, const SalpView& v,
@@ -154,6 +162,7 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
   const int64_t tid = (int64_t)blockIdx.x * 32 + lane;
   const bool live = tid < v.n;
   const int64_t i = live ? (order ? (int64_t)order[tid] : tid) : 0;
+  P4_STAMP(0);
 
   // All four warps read the env's action and state themselves (reads only; every write happens in
   // the dyn warp's epilogue after the block-wide barrier) and derive the same integer plan.
@@ -164,6 +173,7 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
   pp.k_ref = pp.k_T0 = pp.k_jet = pp.upd_a_end = pp.upd_b_begin = pp.upd_b_end = 0;
   if (live) {
     env_step_begin(p, v, io, i, cx, b);
+    P4_STAMP(1);
     Kraw = plan_substeps(cx.plan, v.time_table);
     if (Kraw > 0) pp = make_phase_plan(cx.plan, v.time_table, dv.inv_dt);
   }
@@ -180,6 +190,8 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
   const int nch2 = (Wmax + C - 1) / C;               // chunk c = substeps c C + 1 .. (c + 1) C
   const int nch3 = Kw > 1 ? (Kw - 1 + C - 1) / C : 0;
   const float dir[3] = {(float)cx.plan.dir[0], (float)cx.plan.dir[1], (float)cx.plan.dir[2]};
+  P4_STAMP(2);
+  if ((flags & SALP_P4_FLAG_STAMPS) && blockIdx.x == 0 && warp == 0 && lane == 0) { salp_p4_stamps[8] = Kw; salp_p4_stamps[9] = Wmax; }
   // ring rows of substep j (planes of quads)
   auto row1 = [&](int j) { return ring1 + (j % SALP_P4_SLOTS1) * 2 * 32 + lane; };
   auto row2 = [&](int j) { return ring2 + (j % SALP_P4_SLOTS2) * Q2 * 32 + lane; };
@@ -322,6 +334,7 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
       s.pos0 = s.pos1 = s.pos2 = 0.f; s.ang0 = s.ang1 = s.ang2 = 0.f;
       dyn_step<false, false, AXI>(dv, g, s);
     }
+    P4_STAMP(3);
     // g_j: translational half computed here from the ShapeFront (independent of the motion state: it
     // fills the latency shadows of the recurrence), rotational half from ring 2
     auto coefs_of = [&](int j) {
@@ -400,9 +413,11 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
       flush_body(b, s);
       mixed_finish_dyn(s, b);
     }
+    P4_STAMP(4);
   }
   __syncthreads();
   if (warp != 0) return;
+  P4_STAMP(5);
   const int D = SALP_OBS_BASE + 2 * p.num_obstacles;
   if (live) {
     double t = 0.0;
@@ -421,6 +436,7 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
                  io.terminal_obs ? tile + (32 + lane) * D : nullptr);
   }
   __syncwarp();
+  P4_STAMP(6);
   const int rows = __popc(__ballot_sync(0xffffffffu, live));     // live lanes are the low lanes
   for (int j = lane; j < 32 * D; j += 32) {                      // warp-uniform trip count (D iterations)
     const int r = j / D, k = j - r * D;
@@ -430,6 +446,7 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
       if (io.terminal_obs) io.terminal_obs[e * D + k] = tile[32 * D + j];
     }
   }
+  P4_STAMP(7);
 }
 
 template <bool CHECK>

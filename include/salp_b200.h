@@ -297,6 +297,11 @@ int64_t salp_sizeof_step_io(void);
  * FP32 SIMT figure). */
 int salp_probe_fp32_peak(int device, int millis, double* tflops_out);
 
+/* Diagnostic: salp_step with flag bit 29 (0x20000000) makes block 0 of the small-batch pipeline kernel
+ * record clock64() at the boundaries of its prologue, substep loops and epilogue; this reads the 16
+ * words back (tools/diag_stamps.py explains them).  Synchronises the device. */
+int salp_debug_p4_stamps(long long* out16);
+
 /* ---- rollout-side policy forward (no reference counterpart in src/: the reference's policies live in
  * stable-baselines3; this is SB3's `MlpPolicy` forward as one kernel in front of salp_step) ----------
  * weights_dev: one packed float array -- actor W1[64,D] b1[64] W2[64,64] b2[64] W3[3,64] b3[3], critic
