@@ -170,10 +170,22 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// MUFU.EX2 + MUFU.RCP forms (absolute error ~2e-7, saturating correctly at +-inf): the libm expf / tanhf
-// paths made the epilogue ~200 instructions per hidden unit
-__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float tanhf_(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+// MUFU.EX2 + MUFU.RCP forms, 4-5 instructions each (ex2.approx 2 ulp, rcp.approx 1 ulp; absolute error
+// of the activations ~2e-7; +-inf saturate correctly).  The libm expf / tanhf paths made the epilogue ~200
+// instructions per hidden unit, __expf / __fdividef with their range fix-ups 56; this is ~30, and the
+// ten MUFU per unit are then what bounds the epilogue (XU pipe).
+__device__ __forceinline__ float ex2_(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return rcp_(1.f + ex2_(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanhf_(float x) { return fmaf(-2.f, rcp_(ex2_(2.8853900817779268f * x) + 1.f), 1.f); }
 
 // ------------------------------------------------------------------------------------------------
 // the cell: gates = A W^T (tcgen05), then the element-wise update from TMEM
