@@ -60,7 +60,8 @@ struct P4Layout {
   static constexpr size_t ring3a = ring1 + sizeof(float4) * SALP_P4_SLOTS1 * 2 * 32;           // [SLOTS3][32] float4 (v0 v1 v2 w0)
   static constexpr size_t ring3b = ring3a + sizeof(float4) * SALP_P4_SLOTS3 * 32;              // [SLOTS3][32] float2 (w1 w2)
   static constexpr size_t merge = ring3b + sizeof(float2) * SALP_P4_SLOTS3 * 32;               // [MERGE][32] double
-  static constexpr size_t tags = merge + sizeof(double) * SALP_P4_MERGE * 32;                  // [SLOTS1 + SLOTS2 + SLOTS3][32] int (checked mode)
+  static constexpr size_t snap = merge + sizeof(double) * SALP_P4_MERGE * 32;                  // end-of-cycle snapshots: [2 warps][5][32] float4 + [2 warps][3][32] double2
+  static constexpr size_t tags = snap + 2 * (sizeof(float4) * 5 * 32 + sizeof(double2) * 3 * 32);   // [SLOTS1 + SLOTS2 + SLOTS3][32] int (checked mode)
   static constexpr size_t tile = tags + sizeof(int) * (SALP_P4_SLOTS1 + SALP_P4_SLOTS2 + SALP_P4_SLOTS3) * 32;   // [2][32][D] float
 };
 static inline size_t pipe4_smem_bytes(const SalpParams& p, bool axi) {
@@ -68,38 +69,45 @@ static inline size_t pipe4_smem_bytes(const SalpParams& p, bool axi) {
   return (axi ? P4Layout<true>::tile : P4Layout<false>::tile) + tile;
 }
 
-// Iterations j = j0..je of one hand-off chunk for the lanes whose cycle is still running (j < K),
-// WITHOUT a per-iteration lane test (a `j < K` branch inside the loop costs ~45 cycles of branch /
-// reconvergence latency per substep, as much as the arithmetic of a stage).  A full chunk in which
-// no lane ends runs unrolled as one basic block; otherwise the chunk is cut at the substeps where
-// lanes end (warp-wide min of the remaining K) and each segment runs behind ONE branch.
+// Iterations j = j0..je of one hand-off chunk, for ALL lanes and without any lane test: a full chunk
+// is one unrolled basic block.  Lanes whose cycle has ended (j >= K) simply keep integrating -- their
+// result was put aside when they ended: each consumer warp stores its per-lane state to a snapshot
+// plane in shared memory with PREDICATED stores at the lane's last iteration (j == K - 1; six
+// issue slots per substep, no branch), and its fp64 totals at the flushes the lane was still alive
+// for; after the loops every lane continues from its snapshot.  (Round 2 first cut the chunks at the
+// substeps where lanes end -- warp-wide min of the remaining K, one segment loop per cut --, which cost
+// ~20 us of a 4096-env step: tools/diag_stamps.py, profiles/r02_pipe4_clock_stamps.txt.  A lane test per
+// unrolled iteration was worse still: 0.189 instead of 0.153 ms.)
 // iter(j, at32): at32 = j is a multiple of the 32-substep flush interval (in an unrolled chunk only
 // its last iteration can be, so the other seven stay free of branches).
-// `dn` (warp-uniform, carried across chunks, start at 0): the first cycle end beyond the current
-// position -- recomputed by a warp reduction only after a lane has ended.  Branches are what a lone
-// warp pays for (~30 cycles each): the common chunk (full, nobody ends) costs two.
 template <class Iter>
-__device__ __forceinline__ void p4_run_chunk(int j0, int je, int K, int& dn, Iter&& iter) {
+__device__ __forceinline__ void p4_run_chunk(int j0, int je, Iter&& iter) {
   constexpr int C = SALP_P4_CHUNK;
   static_assert(SALP_MIXED_CHUNK % C == 0, "flush positions must fall on the last iteration of a chunk");
-  if (dn > je && je - j0 + 1 == C) {
-    if (K > je) {
+  if (je - j0 + 1 == C) {
 #pragma unroll
-      for (int u = 0; u < C; u++) iter(j0 + u, u == C - 1 && (je & (SALP_MIXED_CHUNK - 1)) == 0);
-    }
+    for (int u = 0; u < C; u++) iter(j0 + u, u == C - 1 && (je & (SALP_MIXED_CHUNK - 1)) == 0);
     return;
   }
-  int a = j0;
-  while (a <= je) {
-    if (dn <= a) dn = __reduce_min_sync(0xffffffffu, K > a ? K : 0x7fffffff);
-    if (dn == 0x7fffffff) break;                                             // nobody left
-    const int e = dn - 1 < je ? dn - 1 : je;
-    if (K > a) {
 #pragma unroll 1
-      for (int j = a; j <= e; j++) iter(j, (j & (SALP_MIXED_CHUNK - 1)) == 0);
-    }
-    a = e + 1;
-  }
+  for (int j = j0; j <= je; j++) iter(j, (j & (SALP_MIXED_CHUNK - 1)) == 0);
+}
+// predicated 16-byte shared-memory store (a select-free, branch-free "if (p) *dst = v")
+__device__ __forceinline__ void p4_sts128_if(bool p, void* dst, float x, float y, float z, float w) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
+      "f"(x), "f"(y), "f"(z), "f"(w), "r"((int)p)
+      : "memory");
+}
+__device__ __forceinline__ void p4_sts128_if(bool p, void* dst, double x, double y) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %3, 0;\n\t"
+      "@q st.shared.v2.f64 [%0], {%1, %2};\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
+      "d"(x), "d"(y), "r"((int)p)
+      : "memory");
 }
 
 // CHECK (SALP_STEP_CHECK_HANDOFF): every ring row carries the substep index it was written for, in a
@@ -131,6 +139,10 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
   float4* ring3a = reinterpret_cast<float4*>(smem + L::ring3a);
   float2* ring3b = reinterpret_cast<float2*>(smem + L::ring3b);
   double* merge = reinterpret_cast<double*>(smem + L::merge);
+  float4* snap_dyn = reinterpret_cast<float4*>(smem + L::snap);                 // [5][32]
+  float4* snap_kin = snap_dyn + 5 * 32;                                          // [5][32]
+  double2* tot_dyn = reinterpret_cast<double2*>(snap_kin + 5 * 32);             // [3][32]
+  double2* tot_kin = tot_dyn + 3 * 32;                                           // [3][32]
   int* tags1 = reinterpret_cast<int*>(smem + L::tags);
   int* tags2 = tags1 + SALP_P4_SLOTS1 * 32;
   int* tags3 = tags2 + SALP_P4_SLOTS2 * 32;
@@ -196,8 +208,8 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
   auto row1 = [&](int j) { return ring1 + (j % SALP_P4_SLOTS1) * 2 * 32 + lane; };
   auto row2 = [&](int j) { return ring2 + (j % SALP_P4_SLOTS2) * Q2 * 32 + lane; };
   auto put_tag = [&](int* plane, int slots, int j) { if (CHECK) plane[(j % slots) * 32 + lane] = j; };
-  auto check_tag = [&](const int* plane, int slots, int j) {
-    if (CHECK && plane[(j % slots) * 32 + lane] != j) raise_status(v, SALP_ERR_HANDOFF);
+  auto check_tag = [&](const int* plane, int slots, int j, bool mine = true) {     // mine: a row was produced for this lane
+    if (CHECK && mine && plane[(j % slots) * 32 + lane] != j) raise_status(v, SALP_ERR_HANDOFF);
   };
 
   if (warp == 3) {
@@ -300,23 +312,50 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
       mixed_init_kin(b, s);
       dyn_step<false, false, AXI>(dv, g, s);
     }
+    // snapshot of this warp's per-lane state (20 floats) / fp64 totals, see p4_run_chunk
+    auto put_state = [&](bool pr) {
+      p4_sts128_if(pr, snap_kin + 0 * 32 + lane, s.v0, s.v1, s.v2, s.w0);
+      p4_sts128_if(pr, snap_kin + 1 * 32 + lane, s.w1, s.w2, s.phi_lo, s.theta_lo);
+      p4_sts128_if(pr, snap_kin + 2 * 32 + lane, s.psi_lo, s.sph, s.cph, s.sth);
+      p4_sts128_if(pr, snap_kin + 3 * 32 + lane, s.cth, s.sps, s.cps, s.pw0);
+      p4_sts128_if(pr, snap_kin + 4 * 32 + lane, s.pw1, s.pw2, s.vw0, s.vw1);
+    };
+    auto put_totals = [&](bool pr) {
+      p4_sts128_if(pr, tot_kin + 0 * 32 + lane, b.eul[0], b.eul[1]);
+      p4_sts128_if(pr, tot_kin + 1 * 32 + lane, b.eul[2], b.pw[0]);
+      p4_sts128_if(pr, tot_kin + 2 * 32 + lane, b.pw[1], b.pw[2]);
+    };
+    put_state(true);                                            // (a lane with K = 1 ends here)
+    put_totals(true);
     // iteration j: kin step j - 1 on the (v, w) in registers, then the (v, w) of step j from the ring
     auto kin_iter = [&](int j, bool at32) {
       const float4 a = ring3a[(j % SALP_P4_SLOTS3) * 32 + lane];
       const float2 bb = ring3b[(j % SALP_P4_SLOTS3) * 32 + lane];
       check_tag(tags3, SALP_P4_SLOTS3, j);
       kin_world(dv, s);
-      if (at32) flush_world(b, s);
+      if (at32) {
+        flush_world(b, s);
+        put_totals(K > j);
+      }
       s.v0 = a.x; s.v1 = a.y; s.v2 = a.z; s.w0 = a.w; s.w1 = bb.x; s.w2 = bb.y;
+      put_state(j + 1 == K);
     };
-    int dn = 0;
     for (int c = 0; c < nch3; c++) {
       pipe_bar_sync(P4_FULL3(c % SALP_P4_NBUF3));
-      p4_run_chunk(c * C + 1, (c + 1) * C < Kw - 1 ? (c + 1) * C : Kw - 1, K, dn, kin_iter);
+      p4_run_chunk(c * C + 1, (c + 1) * C < Kw - 1 ? (c + 1) * C : Kw - 1, kin_iter);
       __syncwarp();
       pipe_bar_arrive(P4_EMPTY3(c % SALP_P4_NBUF3));
     }
     if (K > 0) {
+      {                                                         // continue from where this lane's cycle ended
+        const float4 q0 = snap_kin[0 * 32 + lane], q1 = snap_kin[1 * 32 + lane], q2 = snap_kin[2 * 32 + lane],
+                     q3 = snap_kin[3 * 32 + lane], q4 = snap_kin[4 * 32 + lane];
+        s.v0 = q0.x; s.v1 = q0.y; s.v2 = q0.z; s.w0 = q0.w; s.w1 = q1.x; s.w2 = q1.y; s.phi_lo = q1.z; s.theta_lo = q1.w;
+        s.psi_lo = q2.x; s.sph = q2.y; s.cph = q2.z; s.sth = q2.w; s.cth = q3.x; s.sps = q3.y; s.cps = q3.z; s.pw0 = q3.w;
+        s.pw1 = q4.x; s.pw2 = q4.y; s.vw0 = q4.z; s.vw1 = q4.w;
+        const double2 t0 = tot_kin[0 * 32 + lane], t1 = tot_kin[1 * 32 + lane], t2 = tot_kin[2 * 32 + lane];
+        b.eul[0] = t0.x; b.eul[1] = t0.y; b.eul[2] = t1.x; b.pw[0] = t1.y; b.pw[1] = t2.x; b.pw[2] = t2.y;
+      }
       kin_world(dv, s);                                         // step K - 1
       flush_world(b, s);
       merge[9 * 32 + lane] = b.eul[0]; merge[10 * 32 + lane] = b.eul[1]; merge[11 * 32 + lane] = b.eul[2];
@@ -341,10 +380,25 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
       ShapeFront f;
       front_load(f, row1(j));
       coef_load_R<AXI>(g, row2(j));
-      check_tag(tags1, SALP_P4_SLOTS1, j);
-      check_tag(tags2, SALP_P4_SLOTS2, j);
+      check_tag(tags1, SALP_P4_SLOTS1, j, j < K);             // (the producers stop at each lane's own K)
+      check_tag(tags2, SALP_P4_SLOTS2, j, j < K);
       make_coefs_T<AXI>(dv, dir, f, g);
     };
+    // snapshot of this warp's per-lane state (18 floats) / fp64 totals, see p4_run_chunk
+    auto put_state = [&](bool pr) {
+      p4_sts128_if(pr, snap_dyn + 0 * 32 + lane, s.v0, s.v1, s.v2, s.w0);
+      p4_sts128_if(pr, snap_dyn + 1 * 32 + lane, s.w1, s.w2, s.ac0, s.ac1);
+      p4_sts128_if(pr, snap_dyn + 2 * 32 + lane, s.ac2, s.al0, s.al1, s.al2);
+      p4_sts128_if(pr, snap_dyn + 3 * 32 + lane, s.pos0, s.pos1, s.pos2, s.ang0);
+      p4_sts128_if(pr, snap_dyn + 4 * 32 + lane, s.ang1, s.ang2, 0.f, 0.f);
+    };
+    auto put_totals = [&](bool pr) {
+      p4_sts128_if(pr, tot_dyn + 0 * 32 + lane, b.pos[0], b.pos[1]);
+      p4_sts128_if(pr, tot_dyn + 1 * 32 + lane, b.pos[2], b.ang[0]);
+      p4_sts128_if(pr, tot_dyn + 2 * 32 + lane, b.ang[1], b.ang[2]);
+    };
+    put_state(true);                                            // (a lane with K = 1 ends here)
+    put_totals(true);
     auto hand_over = [&](int j) {
       ring3a[(j % SALP_P4_SLOTS3) * 32 + lane] = make_float4(s.v0, s.v1, s.v2, s.w0);
       ring3b[(j % SALP_P4_SLOTS3) * 32 + lane] = make_float2(s.w1, s.w2);
@@ -356,33 +410,44 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
       kin_body(dv, s);
       dyn_step<false, false, AXI>(dv, g, s);
       hand_over(j);
-      if (at32) flush_body(b, s);
+      if (at32) {
+        flush_body(b, s);
+        put_totals(K > j);
+      }
+      put_state(j + 1 == K);
     };
     auto dyn_iter_moving = [&](int j, bool at32) {       // the one chunk in which the warp's shape motion ends (W)
       if (j <= WA) coefs_of(j);
       kin_body(dv, s);
       dyn_step<false, false, AXI>(dv, g, s);            // (j > W: com_rate = com_acc = 0, same bits as the static form)
       hand_over(j);
-      if (at32) flush_body(b, s);
+      if (at32) {
+        flush_body(b, s);
+        put_totals(K > j);
+      }
+      put_state(j + 1 == K);
     };
     auto dyn_iter_static = [&](int j, bool at32) {       // the coast: coefficients stay in registers
       kin_body(dv, s);
       dyn_step<false, true, AXI>(dv, g, s);
       hand_over(j);
-      if (at32) flush_body(b, s);
+      if (at32) {
+        flush_body(b, s);
+        put_totals(K > j);
+      }
+      put_state(j + 1 == K);
     };
     // Three loops instead of one with per-chunk conditions (a lone warp pays ~30 cycles per branch):
     //   A  chunks whose substeps all use fresh coefficients (the shape moves),
     //   W  the chunks up to nch2 (the one in which the warp's shape motion ends; producers' last chunk),
     //   B  the coast: coefficients stay in registers, only ring 3 is fed.
-    int dn = 0;
     int c = 0;
     auto chunk_end = [&](int cc) { return (cc + 1) * C < Kw - 1 ? (cc + 1) * C : Kw - 1; };
     const int nA = WA / C < nch3 ? WA / C : nch3;              // chunks with je <= WA (and ring-3 traffic)
     for (; c < nA; c++) {
       pipe_bar_sync(P4_FULL2(c % SALP_P4_NBUF2));              // (ring 1 chunk c was full before ring 2 chunk c)
       if (c >= SALP_P4_NBUF3) pipe_bar_sync(P4_EMPTY3(c % SALP_P4_NBUF3));
-      p4_run_chunk(c * C + 1, (c + 1) * C, K, dn, dyn_iter_load);
+      p4_run_chunk(c * C + 1, (c + 1) * C, dyn_iter_load);
       __syncwarp();
       pipe_bar_arrive(P4_EMPTY1(c % SALP_P4_NBUF1), 96);
       pipe_bar_arrive(P4_EMPTY2(c % SALP_P4_NBUF2));
@@ -391,24 +456,36 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
     for (; c < nch2; c++) {
       pipe_bar_sync(P4_FULL2(c % SALP_P4_NBUF2));
       if (c < nch3 && c >= SALP_P4_NBUF3) pipe_bar_sync(P4_EMPTY3(c % SALP_P4_NBUF3));
-      p4_run_chunk(c * C + 1, chunk_end(c), K, dn, dyn_iter_moving);
+      p4_run_chunk(c * C + 1, chunk_end(c), dyn_iter_moving);
       __syncwarp();
       pipe_bar_arrive(P4_EMPTY1(c % SALP_P4_NBUF1), 96);
       pipe_bar_arrive(P4_EMPTY2(c % SALP_P4_NBUF2));
       if (c < nch3) pipe_bar_arrive(P4_FULL3(c % SALP_P4_NBUF3));
     }
     for (; c < nch3 && c < SALP_P4_NBUF3; c++) {               // (only when the shape motion ends within the first chunks)
-      p4_run_chunk(c * C + 1, chunk_end(c), K, dn, dyn_iter_static);
+      p4_run_chunk(c * C + 1, chunk_end(c), dyn_iter_static);
       __syncwarp();
       pipe_bar_arrive(P4_FULL3(c % SALP_P4_NBUF3));
     }
     for (; c < nch3; c++) {
       pipe_bar_sync(P4_EMPTY3(c % SALP_P4_NBUF3));
-      p4_run_chunk(c * C + 1, chunk_end(c), K, dn, dyn_iter_static);
+      p4_run_chunk(c * C + 1, chunk_end(c), dyn_iter_static);
       __syncwarp();
       pipe_bar_arrive(P4_FULL3(c % SALP_P4_NBUF3));
     }
+    {   // the fp64 totals as of this lane's last flush (ALL lanes: one with K = 0 rode along through its
+        // neighbours' flushes too, and this warp's b goes straight into the epilogue)
+      const double2 t0 = tot_dyn[0 * 32 + lane], t1 = tot_dyn[1 * 32 + lane], t2 = tot_dyn[2 * 32 + lane];
+      b.pos[0] = t0.x; b.pos[1] = t0.y; b.pos[2] = t1.x; b.ang[0] = t1.y; b.ang[1] = t2.x; b.ang[2] = t2.y;
+    }
     if (K > 0) {
+      {                                                         // continue from where this lane's cycle ended
+        const float4 q0 = snap_dyn[0 * 32 + lane], q1 = snap_dyn[1 * 32 + lane], q2 = snap_dyn[2 * 32 + lane],
+                     q3 = snap_dyn[3 * 32 + lane], q4 = snap_dyn[4 * 32 + lane];
+        s.v0 = q0.x; s.v1 = q0.y; s.v2 = q0.z; s.w0 = q0.w; s.w1 = q1.x; s.w2 = q1.y; s.ac0 = q1.z; s.ac1 = q1.w;
+        s.ac2 = q2.x; s.al0 = q2.y; s.al1 = q2.z; s.al2 = q2.w; s.pos0 = q3.x; s.pos1 = q3.y; s.pos2 = q3.z; s.ang0 = q3.w;
+        s.ang1 = q4.x; s.ang2 = q4.y;
+      }
       kin_body(dv, s);                                          // step K - 1
       flush_body(b, s);
       mixed_finish_dyn(s, b);
