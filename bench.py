@@ -453,7 +453,7 @@ def run_cuda_arm(args):
     sweep = None
     if not args.no_sweep:
         sweep = []
-        for ne in (1024, 16384, 65536, 262144, 1048576):
+        for ne in (1024, 8192, 16384, 65536, 262144, 1048576):     # (8192 and 16384: BASELINE configs 4 and 3)
             b = make_batch(ne)
             p = action_pool(ne, A=8)
             st = max(5, min(40, int(4e6 // ne) + 5))

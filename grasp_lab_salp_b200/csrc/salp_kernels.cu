@@ -129,14 +129,17 @@ int salp_launch_step(const SalpParams& p, const SalpView& v, const SalpStepIO& i
   const int block = block_for(v.n);
   // Small batches: the warp-specialised pipeline kernel (salp_pipe4_kernel.cuh), natural or K-sorted
   // order, unless SALP_STEP_FUSED asks for the one-warp kernel.  Up to one 32-env block per SM (4736
-  // envs) it is 1.27x faster than the fused kernel; with two co-resident blocks per SM, the second one
-  // with rotated warp roles, still 1.14x at 5120 and 1.07x at 8192 envs, and level at ~9150 (the
-  // producers of the two blocks share sub-partitions while the shape moves): used up to 56 envs per
-  // SM.  SALP_PIPE_BLOCKS_PER_SM=1 restores the one-block limit (experiment switch).
+  // envs) it is 1.39x faster than the fused kernel (131.5 vs 182.8 us per uniform-random step, L2 warm);
+  // with two co-resident blocks per SM, the second one with rotated warp roles, still 1.20x at 6144,
+  // 1.16x at 8192 and 1.06x at 9472 envs (the producers of the two blocks share sub-partitions while the
+  // shape moves): used up to two full blocks per SM, 64 envs.  A third block does not fit the register
+  // file.  SALP_PIPE_BLOCKS_PER_SM=1 restores the one-block limit, SALP_PIPE_ENVS_PER_SM moves the upper
+  // one (experiment switches).
   const int sms = v.sm_count > 0 ? v.sm_count : 148;
   const bool pipe_ok = p.precision == SALP_PRECISION_MIXED && p.randomization == 0 && !(flags & SALP_STEP_FUSED);
   static const int pipe_blocks_per_sm = [] { const char* e = getenv("SALP_PIPE_BLOCKS_PER_SM"); return e ? atoi(e) : 2; }();
-  const int64_t pipe_max_envs = (int64_t)sms * (pipe_blocks_per_sm >= 2 ? 56 : 32);
+  static const int pipe_envs_per_sm = [] { const char* e = getenv("SALP_PIPE_ENVS_PER_SM"); return e ? atoi(e) : 64; }();
+  const int64_t pipe_max_envs = (int64_t)sms * (pipe_blocks_per_sm >= 2 ? pipe_envs_per_sm : 32);
   if (pipe_ok && v.n <= pipe_max_envs) {
     static bool configured4[64] = {};
     int dev = 0;

@@ -149,7 +149,7 @@ __device__ __forceinline__ void salp_pipe4_body(const SalpParams& p, const SalpD
   float* tile = reinterpret_cast<float*>(smem + L::tile);
   const int lane = threadIdx.x & 31;
   // Role of this warp: 0 dyn, 1 kin, 2 coefs R, 3 front, one per SM sub-partition.  With two blocks
-  // per SM (4737-8288 envs; flags bit 30, set by the launcher) the block that arrives second on its SM
+  // per SM (4737-9472 envs; flags bit 30, set by the launcher) the block that arrives second on its SM
   // rotates its roles by two, so that during the coast -- when only dyn and kin are busy -- the four
   // busy warps of the two co-resident blocks sit on four different sub-partitions: 110 instead of 185
   // cycles per coast substep.  Two things had to be measured to get there: the sub-partition of a warp

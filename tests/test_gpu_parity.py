@@ -304,9 +304,9 @@ def test_axisymmetric_form_equals_general_form(n, pipeline):
     b.check()
 
 
-@pytest.mark.parametrize("n", [6001, 8288])
+@pytest.mark.parametrize("n", [6001, 9472])
 def test_pipeline_kernel_two_blocks_per_sm_matches_fused_kernel(n):
-    """4737-8288 envs: two pipeline blocks share an SM and the second one rotates its warp roles
+    """4737-9472 envs: two pipeline blocks share an SM and the second one rotates its warp roles
     (hardware warp slot + per-SM ticket, salp_pipe4_kernel.cuh).  Whatever roles the warps draw, the
     result is the fused kernel's, bit for bit; the hand-off tags are checked on the way."""
     from grasp_lab_salp_b200.params import FIELDS
