@@ -392,11 +392,13 @@ int salp_lstm_cell(const void* packed_dev, const float* bias_dev, const float* o
   const int64_t n_pad = (n + LSTM_BM - 1) / LSTM_BM * LSTM_BM;
   if (n_pad / LSTM_BM > 0x7fffffff) return SALP_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};                  // (the attribute is per device)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return SALP_ERR_CUDA;
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     if (cudaFuncSetAttribute(salp_lstm_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LSTM_SMEM) != cudaSuccess)
       return SALP_ERR_CUDA;
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   CUtensorMap map_a, map_w;
   if (!lstm_make_map(&map_a, scratch_dev, (uint64_t)n_pad) || !lstm_make_map(&map_w, packed_dev, LSTM_G)) return SALP_ERR_CUDA;

@@ -290,3 +290,20 @@ def test_recurrent_rollout_on_tensor_core_cells_tracks_torch_rollout():
     assert torch.equal(outs[0]["obs"][0], outs[1]["obs"][0])
     assert (outs[0]["val"][0] - outs[1]["val"][0]).abs().max().item() < 2e-2
     assert (outs[0]["act"][0] - outs[1]["act"][0]).abs().max().item() < 2e-2
+
+
+def test_tensor_core_lstm_cell_has_no_cpu_path():
+    """The rollout-side LSTM cell is CUDA only: on CPU parameters the wrapper refuses loudly, and the
+    recurrent trainer then keeps the torch cells (fused_policy is a CUDA-only switch)."""
+    from torch import nn
+    from grasp_lab_salp_b200.lstm import LstmCellB200
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        LstmCellB200(nn.LSTMCell(10, 256), 8)
+    with pytest.raises(ValueError):
+        LstmCellB200(nn.LSTMCell(10, 128), 8)
+    from grasp_lab_salp_b200 import _lib
+    lib = _lib.load()
+    assert lib.salp_lstm_weight_bytes() == 1024 * 320 * 2
+    assert lib.salp_lstm_scratch_bytes(1) == 128 * 320 * 2 and lib.salp_lstm_scratch_bytes(129) == 256 * 320 * 2
+    assert lib.salp_lstm_cell(None, None, None, None, None, None, None, None, None, 8, 10, 256, None) == _lib.ERR_INVALID
+    assert lib.salp_lstm_pack_weights(None, None, None, None, 10, 256, None, None, None) == _lib.ERR_INVALID
