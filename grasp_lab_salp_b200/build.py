@@ -26,6 +26,7 @@ UNITS = {
     "salp_capi.cu": [],
     "salp_policy.cu": [],
     "salp_lstm.cu": [],                    # tcgen05 / TMA LSTM cell (needs the sm_100a target)
+    "salp_lstm_train.cu": [],              # element-wise halves of the learner's LSTM step
 }
 
 

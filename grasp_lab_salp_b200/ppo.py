@@ -160,6 +160,8 @@ class PPOConfig:
     fused_policy: bool = True         # MLP policy on CUDA: the rollout-side forward (both networks, sampling, log-prob,
                                       # clip) is ONE hand-written kernel, salp_mlp_act (csrc/salp_policy.cu); LSTM policy
                                       # on CUDA: both rollout-side LSTM cells run on the tensor cores (csrc/salp_lstm.cu)
+    fused_sequence: bool = True       # RecurrentPPO update: both LSTMs over the whole rollout as lstm_seq.LstmSequence
+                                      # (two launches per cell, step and direction) instead of nn.LSTMCell stepped T times
     cuda_graphs: bool = False         # MLP PPO on CUDA: replay the whole rollout and each minibatch step as CUDA graphs
     seed: int = 0
     hidden: tuple = (64, 64)
@@ -541,6 +543,20 @@ class LstmPolicy(nn.Module):
         hc, _ = self.lstm_critic(obs, (state[2], state[3]))
         return self.critic(hc).squeeze(-1)
 
+    def sequence(self, obs, state, starts):
+        """The T steps of `step` at once for the learner: obs [T, B, D], starts [T, B] -> (mean [T, B, A],
+        value [T, B]).  Both LSTMs run as lstm_seq.LstmSequence (one GEMM + one hand-written element-wise
+        kernel per cell, step and direction; input projection and weight gradients batched over T x B),
+        the 64-64 heads once on the stacked hidden states."""
+        from .lstm_seq import lstm_sequence
+        T, B = starts.shape
+        keep = 1.0 - starts.float()
+        ha = lstm_sequence(self.lstm_actor, obs, state[0], state[1], keep)
+        hc = lstm_sequence(self.lstm_critic, obs, state[2], state[3], keep)
+        mean = self.actor(ha.reshape(T * B, -1)).view(T, B, -1)
+        val = self.critic(hc.reshape(T * B, -1)).view(T, B)
+        return mean, val
+
 
 class RecurrentPPO(PPO):
     """PPO with the LSTM policy.  Rollouts carry the per-env LSTM state (reset on done); the
@@ -675,12 +691,15 @@ class RecurrentPPO(PPO):
         T = roll["logp"].shape[0]
         state = tuple(x[idx] for x in roll["init_state"])
         obs, starts = roll["obs"][:, idx], roll["starts"][:, idx]
-        means, vals = [], []
-        for t in range(T):
-            m, v, state = self.policy.step(obs[t], state, starts[t])
-            means.append(m)
-            vals.append(v)
-        mean, val = torch.stack(means), torch.stack(vals)
+        if cfg.fused_sequence:
+            mean, val = self.policy.sequence(obs, state, starts)
+        else:
+            means, vals = [], []
+            for t in range(T):
+                m, v, state = self.policy.step(obs[t], state, starts[t])
+                means.append(m)
+                vals.append(v)
+            mean, val = torch.stack(means), torch.stack(vals)
         log_std = self.policy.log_std
         z = (roll["act"][:, idx] - mean) * (-log_std).exp()
         logp = (-0.5 * z.pow(2) - log_std - 0.5 * math.log(2 * math.pi)).sum(-1)

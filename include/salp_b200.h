@@ -336,6 +336,22 @@ int salp_lstm_cell(const void* packed_dev, const float* bias_dev, const float* o
                    int64_t n, int32_t obs_dim, int32_t hidden, void* stream);
 int salp_lstm_check(void);
 
+/* ---- the element-wise halves of the LEARNER's LSTM step (RecurrentPPO update, BPTT; fp32, any hidden
+ * size; csrc/salp_lstm_train.cu, used by grasp_lab_salp_b200/lstm_seq.py's autograd.Function) -----------
+ * forward : gates [B, 4H] (torch order i, f, g, o; biases and both products already summed) ->
+ *   act [B, 4H] = (sigmoid i, sigmoid f, tanh g, sigmoid o), c_out = f (c_prev keep_cur) + i g,
+ *   h_out = o tanh(c_out), hm_next = h_out keep_next (the next step's GEMM operand; may be NULL).
+ *   keep_* : float [B] (1 - episode_start) or NULL (= 1).
+ * backward: dh = dh_ext + dh_rec keep_next (either may be NULL), dc_next (NULL = 0), the forward's act /
+ *   c_cur (= its c_out) / c_prev / keep_cur -> dgates [B, 4H], dc_prev = dc f keep_cur. */
+int salp_lstm_pointwise_fwd(const float* gates_dev, const float* c_prev_dev, const float* keep_cur_dev,
+                            const float* keep_next_dev, int64_t batch, int32_t hidden, float* act_dev, float* c_out_dev,
+                            float* h_out_dev, float* hm_next_dev, void* stream);
+int salp_lstm_pointwise_bwd(const float* dh_ext_dev, const float* dh_rec_dev, const float* keep_next_dev,
+                            const float* dc_next_dev, const float* act_dev, const float* c_cur_dev, const float* c_prev_dev,
+                            const float* keep_cur_dev, int64_t batch, int32_t hidden, float* dgates_dev, float* dc_prev_dev,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

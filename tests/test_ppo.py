@@ -307,3 +307,48 @@ def test_tensor_core_lstm_cell_has_no_cpu_path():
     assert lib.salp_lstm_scratch_bytes(1) == 128 * 320 * 2 and lib.salp_lstm_scratch_bytes(129) == 256 * 320 * 2
     assert lib.salp_lstm_cell(None, None, None, None, None, None, None, None, None, 8, 10, 256, None) == _lib.ERR_INVALID
     assert lib.salp_lstm_pack_weights(None, None, None, None, 10, 256, None, None, None) == _lib.ERR_INVALID
+
+
+def _sequence_vs_step_loop(device, T=7, B=13, tol=2e-5):
+    """LstmPolicy.sequence (lstm_seq.LstmSequence) against the nn.LSTMCell step loop: outputs and the
+    gradient of every parameter."""
+    from grasp_lab_salp_b200.ppo import LstmPolicy
+    torch.manual_seed(11)
+    pol = LstmPolicy(10, 3).to(device)
+    obs = torch.randn(T, B, 10, device=device)
+    starts = torch.rand(T, B, device=device) < 0.25
+    starts[0, ::2] = True
+    state = tuple(torch.randn(B, 256, device=device) * 0.5 for _ in range(4))
+    wm, wv = torch.randn(T, B, 3, device=device), torch.randn(T, B, device=device)
+
+    def loss_of(mean, val):
+        return (mean * wm).sum() + (val * wv).sum() + (mean ** 2).sum()
+
+    means, vals, st = [], [], state
+    for t in range(T):
+        m, v, st = pol.step(obs[t], st, starts[t])
+        means.append(m)
+        vals.append(v)
+    m1, v1 = torch.stack(means), torch.stack(vals)
+    pol.zero_grad()
+    loss_of(m1, v1).backward()
+    g1 = {k: p.grad.clone() for k, p in pol.named_parameters() if p.grad is not None}
+    m2, v2 = pol.sequence(obs, state, starts)
+    pol.zero_grad()
+    loss_of(m2, v2).backward()
+    g2 = {k: p.grad.clone() for k, p in pol.named_parameters() if p.grad is not None}
+    assert (m1 - m2).abs().max().item() < tol and (v1 - v2).abs().max().item() < tol
+    assert set(g1) == set(g2) and len(g1) >= 20
+    for k in g1:
+        scale = max(1.0, g1[k].abs().max().item())
+        assert (g1[k] - g2[k]).abs().max().item() < tol * scale, k
+
+
+def test_lstm_sequence_function_matches_cell_loop_cpu():
+    _sequence_vs_step_loop("cpu")
+
+
+@pytest.mark.gpu
+def test_lstm_sequence_function_matches_cell_loop_gpu():
+    """The same with the hand-written element-wise kernels (csrc/salp_lstm_train.cu) on the GPU."""
+    _sequence_vs_step_loop("cuda", T=32, B=512, tol=1e-4)
