@@ -122,14 +122,19 @@ def test_recurrent_ppo_improves_on_gpu():
     the round-1 curve FELL (success 25 % -> 4 % at 30 M steps: with +-500 rewards the critic's gradient
     swamped the global gradient-norm clip and the actor's clipped gradient fell below Adam's eps).
     With the learner-side reward normalisation (PPOConfig.normalize_reward) it passes the MLP policy's
-    10 M-step level (~45 % success) within 9 M env-steps; the raw episode return rises with it."""
+    10 M-step level (~45 % success) within 11 M env-steps; the raw episode return rises with it.
+    (Three seed-identical runs that differ only in floating-point summation order -- fp32 torch cells,
+    tensor-core rollout cells, sequence-function learner -- stood at 58 / 65 / 46 % after 9 M env-steps
+    and at 88.3 / 88.0 / 87.0 % after 20 M: training is chaotic in its details, not in its outcome;
+    the "timeout wave" of 500-cycle episodes ending around 8.2 M env-steps makes 9 M a noisy place to
+    look, hence 11 M.)"""
     import torch
     from grasp_lab_salp_b200 import SalpBatch, default_params
     from grasp_lab_salp_b200.ppo import DeviceEnv, PPOConfig, RecurrentPPO
     batch = SalpBatch(8192, default_params(), seed=0)
     algo = RecurrentPPO(DeviceEnv(batch), PPOConfig(n_steps=32, batch_size=16384, cuda_graphs=True, seed=0))
     rows = []
-    algo.learn(9_000_000, log=rows.append)
+    algo.learn(11_000_000, log=rows.append)
     batch.check()
     first, last = rows[0], rows[-1]
     print({k: round(first[k], 3) for k in ("success_rate", "mean_episode_return")},
