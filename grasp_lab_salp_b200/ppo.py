@@ -545,14 +545,13 @@ class LstmPolicy(nn.Module):
 
     def sequence(self, obs, state, starts):
         """The T steps of `step` at once for the learner: obs [T, B, D], starts [T, B] -> (mean [T, B, A],
-        value [T, B]).  Both LSTMs run as lstm_seq.LstmSequence (one GEMM + one hand-written element-wise
-        kernel per cell, step and direction; input projection and weight gradients batched over T x B),
+        value [T, B]).  Both LSTMs run side by side as ONE lstm_seq.LstmSequence (one batched GEMM + one hand-written
+        element-wise kernel per step and direction; input projection and weight gradients batched over T x B),
         the 64-64 heads once on the stacked hidden states."""
         from .lstm_seq import lstm_sequence
         T, B = starts.shape
         keep = 1.0 - starts.float()
-        ha = lstm_sequence(self.lstm_actor, obs, state[0], state[1], keep)
-        hc = lstm_sequence(self.lstm_critic, obs, state[2], state[3], keep)
+        ha, hc = lstm_sequence([self.lstm_actor, self.lstm_critic], obs, [state[0], state[2]], [state[1], state[3]], keep)
         mean = self.actor(ha.reshape(T * B, -1)).view(T, B, -1)
         val = self.critic(hc.reshape(T * B, -1)).view(T, B)
         return mean, val
