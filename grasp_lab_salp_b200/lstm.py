@@ -56,8 +56,8 @@ class LstmCellB200:
         if not (0 < n <= self.n and obs.shape[1] == self.obs_dim and obs.dtype == torch.float32 and obs.is_contiguous()):
             raise ValueError(f"obs must be a contiguous float32 [n <= {self.n}, {self.obs_dim}] tensor")
         for t in (h, c, h_out, c_out):
-            if not (tuple(t.shape) == (n, HIDDEN) and t.dtype == torch.float32 and t.is_contiguous() and t.device == obs.device):
-                raise ValueError(f"h / c must be contiguous float32 [{n}, {HIDDEN}] tensors on the observations' device")
+            if not (tuple(t.shape) == (n, HIDDEN) and t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda):
+                raise ValueError(f"h / c must be contiguous float32 [{n}, {HIDDEN}] CUDA tensors")
         if starts is not None and not (tuple(starts.shape) == (n,) and starts.element_size() == 1 and starts.is_contiguous()):
             raise ValueError("starts must be a contiguous bool / uint8 [n] tensor")
         rc = self.lib.salp_lstm_cell(C.c_void_p(self.packed.data_ptr()), C.c_void_p(self.bias.data_ptr()),
