@@ -81,7 +81,7 @@ def test_two_rank_shards_equal_the_single_process_run():
         np.testing.assert_array_equal(got, ref[t].astype(np.float32))
 
 
-def _ppo_worker(rank, world, port, out):
+def _ppo_worker(rank, world, port, out, recurrent=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
@@ -89,10 +89,13 @@ def _ppo_worker(rank, world, port, out):
     import torch
     from emu_backend import emu_cdll
     from grasp_lab_salp_b200.distributed import make_shard
-    from grasp_lab_salp_b200.ppo import PPO, HostEnv, PPOConfig
+    from grasp_lab_salp_b200.ppo import PPO, HostEnv, PPOConfig, RecurrentPPO
     dist.init_process_group("gloo", rank=rank, world_size=world)
     shard = make_shard(13, seed=2, device=0, _cdll=emu_cdll())            # 7 + 6 envs: uneven shards
-    algo = PPO(HostEnv(shard), PPOConfig(n_steps=4, batch_size=8, n_epochs=2, seed=3))
+    if recurrent:      # minibatches are env sequences: 2 of them per step; BPTT through lstm_seq.LstmSequence
+        algo = RecurrentPPO(HostEnv(shard), PPOConfig(n_steps=4, batch_size=8, n_epochs=2, seed=3))
+    else:
+        algo = PPO(HostEnv(shard), PPOConfig(n_steps=4, batch_size=8, n_epochs=2, seed=3))
     noise = torch.randn(3, generator=algo.gen)                             # per-rank exploration noise
     stats = algo.learn(2 * 4 * 13)
     w = torch.cat([p.detach().reshape(-1) for p in algo.policy.parameters()])
@@ -119,6 +122,26 @@ def test_two_rank_ppo_with_uneven_shards_keeps_ranks_in_step():
         p.join(timeout=60)
         assert p.exitcode == 0
     (w0, z0, calls0, steps0), (w1, z1, calls1, steps1) = gathered
+    np.testing.assert_allclose(w0, w1, rtol=0, atol=1e-7)
+    assert calls0 == calls1 and calls0 > 0
+    assert z0 != z1
+
+
+def test_two_rank_recurrent_ppo_with_uneven_shards_keeps_ranks_in_step():
+    """The same for RecurrentPPO (LSTM policy, sequence-function learner): identical weights on both
+    ranks after two iterations, same number of optimiser steps, per-rank noise."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29800 + os.getpid() % 90
+    procs = [ctx.Process(target=_ppo_worker, args=(r, 2, port, out, True)) for r in range(2)]
+    for p in procs:
+        p.start()
+    gathered = out.get(timeout=400)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (w0, z0, calls0, steps0), (w1, z1, calls1, steps1) = gathered
+    assert len(w0) > 500_000
     np.testing.assert_allclose(w0, w1, rtol=0, atol=1e-7)
     assert calls0 == calls1 and calls0 > 0
     assert z0 != z1
