@@ -26,6 +26,10 @@
 // with the same fixed 32-substep grouping of the fp32 chunk sums, and every operation is explicitly
 // rounded: bit-identical with the fused kernel (tests/test_gpu_parity.py).
 //
+// The 32 lanes of a block end their cycles at different substeps (K is anything in 0..1348).  The
+// consumer warps never test for that inside the loops: a finished lane rides along, its state having
+// been put aside by predicated shared-memory stores at its last substep (p4_run_chunk below).
+//
 // "warp r" above is a ROLE; which hardware warp takes it is decided at the top of the body (two
 // co-resident blocks per SM interleave their roles over the sub-partitions).
 //
