@@ -69,3 +69,18 @@ def test_no_cpu_fallback():
         SalpBatch(8)
     assert e.value.code == _lib.ERR_NO_DEVICE
     assert "no CPU fallback" in str(e.value)
+
+
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/salp_b200.h must compile as C99 (no C++ in the
+    signatures, every type it uses declared)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "salp_b200.h"\nint main(void) { return (int)sizeof(SalpParams) == 0 || (int)sizeof(SalpStepIO) == 0; }\n')
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-c",
+                        str(src), "-o", str(tmp_path / "hdr.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
